@@ -1,0 +1,96 @@
+/*
+ * specbleach-b200 -- EXTRA entry points that the reference does not have.
+ *
+ * The 22 drop-in symbols live in specbleach_denoiser.h and
+ * specbleach_2d_denoiser.h and are untouched.  Everything here is additive
+ * ("Allowed extension"): device selection, pinned host
+ * buffers, device-resident and batched processing, and instrumentation for
+ * bench.py / the parity tests.  Plain C ABI: pointers and sizes only.
+ */
+#ifndef SPECBLEACH_B200_H_INCLUDED
+#define SPECBLEACH_B200_H_INCLUDED
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+typedef void* SpectralBleachHandle;
+
+/* Number of CUDA devices visible to the process (0 if none / no driver). */
+int specbleach_b200_device_count(void);
+
+/* Selects the device used by handles created afterwards on this thread
+ * (one process per GPU is the intended deployment). Returns false on error. */
+bool specbleach_b200_set_device(int device);
+
+/* Last error message of this library (empty string if none). */
+const char* specbleach_b200_last_error(void);
+
+/* Page-locked host buffers: process() detects them and DMA-copies directly. */
+void* specbleach_b200_host_alloc(size_t bytes);
+void specbleach_b200_host_free(void* p);
+
+/* Engine tuning (call before the first handle is created):
+ * frames per internal sub-call (default 4096) and number of lanes, i.e. CUDA
+ * streams with private scratch spectrograms (default 4). */
+bool specbleach_b200_configure(uint32_t chunk_frames, uint32_t lanes);
+
+/* Same contract as specbleach[_2d]_process, but `input`/`output` are DEVICE
+ * pointers on the handle's device; no host copies, returns after the work has
+ * completed.  Works for handles of either denoiser. */
+bool specbleach_b200_process_device(SpectralBleachHandle instance, uint32_t number_of_samples,
+                                    const float* d_input, float* d_output);
+
+/* Processes `count` independent handles (streams/channels), equivalent to
+ * calling specbleach[_2d]_process on each, with host<->device copies and
+ * kernels of different handles overlapped across lanes.  inputs[i]/outputs[i]
+ * are HOST buffers of number_of_samples[i] floats (may alias each other
+ * pairwise). Returns false if any handle failed. */
+bool specbleach_b200_process_batch(SpectralBleachHandle* instances, uint32_t count,
+                                   const uint32_t* number_of_samples,
+                                   const float* const* inputs, float* const* outputs);
+
+/* Device-resident variant of the batch call. */
+bool specbleach_b200_process_batch_device(SpectralBleachHandle* instances, uint32_t count,
+                                          const uint32_t* number_of_samples,
+                                          const float* const* d_inputs,
+                                          float* const* d_outputs);
+
+/* Instrumentation ---------------------------------------------------------- */
+typedef struct SpecbleachB200Stats {
+  uint64_t kernel_launches;    /* kernels launched by this library since reset      */
+  uint64_t nlm_launches;       /* NLM main-kernel launches timed with CUDA events   */
+  double nlm_ms;               /* summed device time of those launches (ms)         */
+  uint64_t nlm_frame_blocks;   /* target frames x 8-bin paste blocks they processed */
+  uint64_t frames;             /* STFT frames processed                             */
+} SpecbleachB200Stats;
+
+/* enable != 0: bracket every NLM launch with CUDA events on its stream. */
+void specbleach_b200_profile(int enable);
+void specbleach_b200_stats_reset(void);
+/* Synchronises the device, folds pending event pairs into the totals. */
+bool specbleach_b200_stats_get(SpecbleachB200Stats* out);
+
+/* Geometry of a handle: frame, fft size, hop, bins (for tests and tools). */
+bool specbleach_b200_get_geometry(SpectralBleachHandle instance, uint32_t* frame,
+                                  uint32_t* fft_size, uint32_t* hop, uint32_t* bins);
+
+/* Single-kernel entry points used by the parity tests (host buffers). ------ */
+/* NLM over a whole SNR map snr[frames][bins] (row-major, pitch = bins):
+ * out[j] = filtered frame j-4 as the reference returns it after pushing frame
+ * j (rows j < 20 are left untouched). */
+bool specbleach_b200_debug_nlm(const float* snr, uint32_t frames, uint32_t bins, float h,
+                               float* out);
+/* Forward real FFT of `frames` rows of fft_size samples each -> FFTW
+ * halfcomplex rows (r0..r_{N/2}, i_{N/2-1}..i_1), then back (unnormalised). */
+bool specbleach_b200_debug_rfft(uint32_t fft_size, uint32_t frames, const float* in,
+                                float* halfcomplex, float* roundtrip);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECBLEACH_B200_H_INCLUDED */

@@ -1,0 +1,38 @@
+// Engine-level declarations shared by sb_engine.cu and sb_api.cu.
+#pragma once
+
+#include "sb_common.h"
+
+namespace sb {
+
+struct Context {
+  int chunk_frames = 4096;   // frames per internal sub-call
+  int num_lanes = 4;
+  std::vector<Lane> lanes;
+  // instrumentation
+  double nlm_ms = 0.0;
+  uint64_t nlm_launches = 0;
+  uint64_t nlm_frame_blocks = 0;
+  uint64_t frames = 0;
+};
+Context& ctx();
+
+void set_error_msg(const char* msg);
+
+Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms);
+void handle_destroy(Handle* h);
+bool handle_load_parameters(Handle* h, const Params& p);
+bool handle_load_profile(Handle* h, const float* prof, uint32_t size, uint32_t blocks, int mode);
+void handle_reset_profile(Handle* h);
+
+Lane* get_lane(int idx, const GeoK& g);
+bool process_call(Handle* h, uint32_t n, const float* in, float* out, bool device_io);
+bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* const* in,
+                   float* const* out, bool device_io);
+bool stats_collect(Context& c);
+
+// sb_geometry.cu: private geometry for the FFT-only debug entry point
+Geometry* make_fft_geometry(int fft_size);
+void free_geometry(Geometry* G);
+
+}  // namespace sb

@@ -1,0 +1,619 @@
+// Gain chain: everything between the (NLM-smoothed) spectrum and the gains that
+// multiply the delayed FFT frame.  Frame-parallel parts are ordinary
+// (frame, bin) / (frame, band) kernels; the three time recursions of the
+// masking veto are one-thread-per-bin / per-band sequential scans over frames.
+//
+// Reference functions restated here (whole-batch form):
+//   get_morphed_profile            spectral_utils.c:253-279
+//   nlm_filter_calculate_snr       nlm_filter.c:453-479
+//   nlm_filter_reconstruct_magnitude nlm_filter.c:481-508
+//   calculate_berouti_per_bin      suppression_engine.c:108-133
+//   tonal_reducer_run / detect_tonal_components  tonal_reducer.c:54-114, tonal_detector.c:24-162
+//   spectral_smoothing_run (FIXED) spectral_smoother.c:111-139,183-192   (1D)
+//   masking_veto_apply             masking_veto.c:127-267
+//   compute_masking_thresholds     masking_estimator.c:188-349
+//   apply_thresholds_as_floor      absolute_hearing_thresholds.c:141-159
+//   wiener_subtraction             gain_calculator.c:27-69
+//   spectral_whitening_get_weights spectral_whitening.c:59-111
+//   noise_floor_manager_apply      noise_floor_manager.c:77-163
+//   denoiser_post_process_apply    denoiser_post_process.c:26-51
+#include "sb_common.h"
+
+#include <float.h>
+
+namespace sb {
+namespace {
+
+constexpr float kInvPower = 1.0f / kPowerLawExp;
+constexpr float kInvAdd = 1.0f / kAdditivityExp;
+
+__global__ void morph_kernel(const GeoK g, const float* __restrict__ prof, float a,
+                             float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.Kp) return;
+  float v = 0.f;
+  if (k < g.K) {
+    const float mean = prof[k], med = prof[g.Kp + k], mx = prof[2 * g.Kp + k],
+                mn = prof[3 * g.Kp + k];
+    if (a < 0.0f) {
+      const float t = -a;
+      v = (mean * (1.0f - t)) + (med * t);
+    } else {
+      v = (mean * (1.0f - a)) + (mx * a);
+    }
+    v = fmaxf(v, mn);
+  }
+  out[k] = v;
+}
+
+__global__ void fill_rows_kernel(const GeoK g, const float* __restrict__ row,
+                                 float* __restrict__ dst, int rows) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.Kp) return;
+  const float v = row[k];
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * g.Kp + k] = v;
+}
+
+__global__ void snr_kernel(const GeoK g, const float* __restrict__ P,
+                           const float* __restrict__ noise, float* __restrict__ S) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t o = (size_t)blockIdx.y * g.Kp + k;
+  if (k >= g.Kp) return;
+  float v = 0.f;
+  if (k < g.K) {
+    const float n = noise[o];
+    const float den = n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin;
+    v = P[o] / den;
+  }
+  S[o] = v;
+}
+
+// 51-bin edge-clamped median over frequency, then the tonal mask.
+__global__ void __launch_bounds__(256)
+tonal_mask_kernel(const GeoK g, const float* __restrict__ det, int det_stride,
+                  float* __restrict__ mask, int mask_stride) {
+  extern __shared__ float sm[];
+  const int row = blockIdx.x;
+  const float* __restrict__ d = det + (size_t)row * det_stride;
+  const int half = kTonalWindow / 2;
+  const int K = g.K;
+  for (int e = threadIdx.x; e < K + 2 * half; e += blockDim.x) {
+    int idx = e - half;
+    idx = idx < 0 ? 0 : (idx > K - 1 ? K - 1 : idx);
+    sm[e] = d[idx];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
+    float m = 0.f;
+    if (k < K) {
+      const float* w = &sm[k];   // window = w[0..50]
+      float med = w[half];
+      for (int i = 0; i < kTonalWindow; i++) {
+        const float v = w[i];
+        int less = 0, leq = 0;
+        for (int j = 0; j < kTonalWindow; j++) {
+          const float u = w[j];
+          less += (u < v);
+          leq += (u <= v);
+        }
+        if (less <= half && half < leq) { med = v; break; }
+      }
+      const float peak = w[half];
+      if (!(peak - med < kMinPeakProminence)) {
+        const float ratio = peak / (med + 1e-20f);
+        if (ratio > kPeakThreshold) m = (peak - med) / (peak + 1e-20f);
+      }
+    }
+    mask[(size_t)row * mask_stride + k] = m;
+  }
+}
+
+// Whitening weights: smooth3(noise) -> median (bitonic sort) -> power-law weights.
+__global__ void __launch_bounds__(512)
+whitening_kernel(const GeoK g, const float* __restrict__ noise, int noise_stride, float whit,
+                 float* __restrict__ wt, int wt_stride, int P2) {
+  extern __shared__ float sm[];
+  float* srt = sm;           // [P2]
+  float* smo = sm + P2;      // [K]
+  const int row = blockIdx.x;
+  const float* __restrict__ n = noise + (size_t)row * noise_stride;
+  const int K = g.K;
+  const float f = 0.5f;
+  for (int k = threadIdx.x; k < P2; k += blockDim.x) {
+    float v = INFINITY;
+    if (k < K) {
+      const float c = n[k];
+      if (K < 2) v = c;
+      else if (k == 0) v = ((c + n[1]) / 2.0f * f) + (c * (1.0f - f));
+      else if (k == K - 1) v = (((n[K - 2] + c) / 2.0f) * f) + (c * (1.0f - f));
+      else v = (((n[k - 1] + c + n[k + 1]) / 3.0f) * f) + (c * (1.0f - f));
+      smo[k] = v;
+    }
+    srt[k] = v;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < P2 / 2; t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const float a = srt[lo], b = srt[hi];
+        if ((a > b) == up) { srt[lo] = b; srt[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  float anchor = srt[K / 2];
+  if (anchor < kSpectralEps) anchor = kSpectralEps;
+  for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
+    float w = 1.0f;
+    if (k < K && whit > 0.0f && smo[k] > kSpectralEps) w = powf(anchor / smo[k], whit);
+    wt[(size_t)row * wt_stride + k] = w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// (frame, bin): magnitude, Berouti alpha, tonal boost, clean-signal estimate
+// ---------------------------------------------------------------------------
+struct PreArgs {
+  int first_active, two_d, mask_stride;
+  float alpha_max_user, tonal_gain;
+};
+
+__global__ void gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
+                                const float* __restrict__ noise_t,
+                                const float* __restrict__ mask, float* __restrict__ Mg,
+                                float* __restrict__ alpha, float* __restrict__ clean) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.Kp) return;
+  const int i = a.first_active + blockIdx.y;
+  const size_t o = (size_t)i * g.Kp + k;
+  if (k >= g.K) {
+    alpha[o] = 1.f;
+    if (a.two_d) { Mg[o] = 0.f; clean[o] = 0.f; }
+    return;
+  }
+  const float n = noise_t[o];
+  float spec;
+  if (a.two_d) {
+    const float den = n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin;
+    spec = ref[o] * den;             // nlm_filter.c:481-508 (ref = smoothed SNR)
+    Mg[o] = spec;
+    clean[o] = fmaxf(spec - n, 0.0f);
+  } else {
+    spec = ref[o];                   // 1D: alpha from the UNsmoothed power (spectral_denoiser.c:298-300)
+  }
+  // suppression_engine.c:108-133
+  const float snr_db = 10.0f * log10f(spec / (n + kSpectralEps));
+  float al;
+  if (snr_db <= kSnrLowDb) al = a.alpha_max_user;
+  else if (snr_db >= kSnrHighDb) al = kAlphaMin;
+  else {
+    const float ns = (snr_db - kSnrLowDb) / (kSnrHighDb - kSnrLowDb);
+    al = a.alpha_max_user - (ns * (a.alpha_max_user - kAlphaMin));
+  }
+  // tonal_reducer.c:92-113
+  if (!(a.tonal_gain >= 0.999f)) {
+    const float m = mask[(size_t)i * a.mask_stride + k];
+    if (m > 0.0f) {
+      const float strength = 1.0f - a.tonal_gain;
+      const float alpha_needed = kAlphaMin + (strength * (kAlphaMaxTonal - kAlphaMin));
+      const float target_alpha = kAlphaMin + m * (alpha_needed - kAlphaMin);
+      al = fmaxf(al, target_alpha);
+    }
+  }
+  alpha[o] = al;
+}
+
+// ---------------------------------------------------------------------------
+// per-bin scans over frames: (1D) release smoothing, then the stabilised
+// clean-signal EMA of the veto (masking_veto.c:137-147)
+// ---------------------------------------------------------------------------
+__global__ void bin_scan_kernel(const GeoK g, int first_active, int active, int two_d,
+                                float smoothing, const float* __restrict__ P,
+                                const float* __restrict__ noise_t, float* __restrict__ Mg,
+                                float* __restrict__ stable, float* __restrict__ st_state,
+                                float* __restrict__ sp_state) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.K) return;
+  float st = st_state[k];
+  if (two_d) {
+    size_t o = (size_t)first_active * g.Kp + k;
+    int f = 0;
+    for (; f + 4 <= active; f += 4) {
+      const float c0 = stable[o], c1 = stable[o + g.Kp], c2 = stable[o + 2 * (size_t)g.Kp],
+                  c3 = stable[o + 3 * (size_t)g.Kp];
+      st = (kVetoSmoothing * c0) + ((1.0f - kVetoSmoothing) * st); stable[o] = st;
+      st = (kVetoSmoothing * c1) + ((1.0f - kVetoSmoothing) * st); stable[o + g.Kp] = st;
+      st = (kVetoSmoothing * c2) + ((1.0f - kVetoSmoothing) * st); stable[o + 2 * (size_t)g.Kp] = st;
+      st = (kVetoSmoothing * c3) + ((1.0f - kVetoSmoothing) * st); stable[o + 3 * (size_t)g.Kp] = st;
+      o += 4 * (size_t)g.Kp;
+    }
+    for (; f < active; f++) {
+      st = (kVetoSmoothing * stable[o]) + ((1.0f - kVetoSmoothing) * st);
+      stable[o] = st;
+      o += g.Kp;
+    }
+  } else {
+    float sp = sp_state[k];
+    size_t o = (size_t)first_active * g.Kp + k;
+    for (int f = 0; f < active; f++) {
+      const float cur = P[o];
+      // spectral_smoother.c:183-192 (release-only smoothing), state update :132-133
+      float v = cur;
+      if (cur > sp) v = (smoothing * sp) + ((1.0f - smoothing) * cur);
+      sp = v;
+      Mg[o] = v;
+      const float c = fmaxf(v - noise_t[o], 0.0f);
+      st = (kVetoSmoothing * c) + ((1.0f - kVetoSmoothing) * st);
+      stable[o] = st;
+      o += g.Kp;
+    }
+    sp_state[k] = sp;
+  }
+  st_state[k] = st;
+}
+
+// ---------------------------------------------------------------------------
+// (frame, band): band energies, spreading, tonality -> a_t[b]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float spreading_gain(float dz, float level_db) {
+  // masking_estimator.c:305-318
+  const float s_up = fminf(fmaxf(15.0f - ((level_db - 40.0f) * 0.2f), 5.0f), 15.0f);
+  const float s_total = (25.0f + s_up) / 2.0f;
+  const float s_offset = (25.0f - s_up) / 2.0f;
+  const float y = dz + 0.474f;
+  const float sf_db = 15.81f + (s_offset * y) - (s_total * sqrtf(1.0f + (y * y)));
+  return powf(10.0f, sf_db / 10.0f);
+}
+
+__global__ void __launch_bounds__(256)
+band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__ stable,
+            const float* __restrict__ Xre_t, const float* __restrict__ noise_t,
+            float* __restrict__ band_a) {
+  __shared__ float E[2][kBandPitch], SL[2][kBandPitch], SV[2][kBandPitch];
+  __shared__ float LV[2][kBandPitch], SPR[2][kBandPitch];
+  const int i = first_active + blockIdx.x;
+  const size_t ro = (size_t)i * g.Kp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < g.nb; b += nw) {
+    float e0 = 0.f, l0 = 0.f, v0 = 0.f, e1 = 0.f, l1 = 0.f, v1 = 0.f;
+    for (int k = g.band_start[b] + lane; k < g.band_start[b + 1]; k += 32) {
+      const float s = stable[ro + k];
+      const float sv = fmaxf(s, kSpectralEps);
+      e0 += s; v0 += sv; l0 += log10f(sv);
+      if (two_d) {
+        const float fu = fmaxf(Xre_t[ro + k] - noise_t[ro + k], 0.0f);   // masking_veto.c:151-157
+        const float fv = fmaxf(fu, kSpectralEps);
+        e1 += fu; v1 += fv; l1 += log10f(fv);
+      }
+    }
+    e0 = warp_sum(e0); l0 = warp_sum(l0); v0 = warp_sum(v0);
+    if (two_d) { e1 = warp_sum(e1); l1 = warp_sum(l1); v1 = warp_sum(v1); }
+    if (lane == 0) {
+      E[0][b] = e0; SL[0][b] = l0; SV[0][b] = v0;
+      E[1][b] = e1; SL[1][b] = l1; SV[1][b] = v1;
+    }
+  }
+  __syncthreads();
+  const int nspec = two_d ? 2 : 1;
+  if (threadIdx.x < nspec * kBandPitch) {
+    const int s = threadIdx.x / kBandPitch, b = threadIdx.x % kBandPitch;
+    if (b < g.nb) LV[s][b] = (10.0f * log10f(E[s][b] + kSpectralEps)) + kDbFsToSpl;
+  }
+  __syncthreads();
+  if (threadIdx.x < nspec * kBandPitch) {
+    const int s = threadIdx.x / kBandPitch, b = threadIdx.x % kBandPitch;
+    if (b < g.nb) {
+      float acc = 0.f;
+      for (int j = 0; j < g.nb; j++) {
+        const float dz = (float)b - (float)j;
+        const float gain = spreading_gain(dz, LV[s][j]);
+        acc += powf(E[s][j] * gain, kAdditivityExp);
+      }
+      const float spr = powf(acc, kInvAdd);
+      // tonality (masking_estimator.c:320-349)
+      const float bins = (float)g.band_start[b + 1] - (float)g.band_start[b];
+      float tf = 1.0f;
+      if (bins > 1.0f) {
+        const float sfm = 10.0f * ((SL[s][b] / bins) - log10f(SV[s][b] / bins));
+        tf = fminf(fmaxf((sfm - 0.0f) / (-60.0f - 0.0f), 0.0f), 1.0f);
+      }
+      const float bark_idx = fminf((float)(b + 1), 25.0f);
+      const float offset = (tf * (14.5f + bark_idx)) + (6.0f * (1.0f - tf));
+      float thr = powf(10.0f, (log10f(spr + kSpectralEps) - (offset / 10.0f)));
+      if (s == 1) thr *= g.bwd;      // backward masking (masking_estimator.c:279-283)
+      SPR[s][b] = powf(thr, kPowerLawExp);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kBandPitch) {
+    const int b = threadIdx.x;
+    float a = 0.f;
+    if (b < g.nb) a = SPR[0][b] + (two_d ? SPR[1][b] : 0.f);
+    band_a[(size_t)i * kBandPitch + b] = a;
+  }
+}
+
+// per-band forward-masking recursion, linear in u = T^0.6:
+//   T = (T_f^p + (T_prev*fwd)^p + (T_fut*bwd)^p)^(1/p)   (masking_estimator.c:270-288)
+__global__ void tscan_kernel(const GeoK g, int first_active, int active,
+                             const float* __restrict__ band_a, float* __restrict__ band_T,
+                             float* __restrict__ u_state) {
+  const int b = threadIdx.x;
+  if (b >= g.nb) return;
+  float u = u_state[b];
+  const float c = g.fwd_pow[b];
+  for (int f = 0; f < active; f++) {
+    const size_t o = (size_t)(first_active + f) * kBandPitch + b;
+    u = fmaf(c, u, band_a[o]);
+    band_T[o] = powf(u, kInvPower);
+  }
+  u_state[b] = u;
+}
+
+// (frame, band): absolute-threshold floor, band NMR -> protection
+__global__ void __launch_bounds__(256)
+nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
+           const float* __restrict__ noise_t, float* __restrict__ band_p) {
+  const int i = first_active + blockIdx.x;
+  const size_t ro = (size_t)i * g.Kp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < g.nb; b += nw) {
+    const float T = band_T[(size_t)i * kBandPitch + b];
+    // absolute_hearing_thresholds.c:141-159
+    const float spl = (10.0f * log10f(T + kSpectralEps)) + g.spl_ref;
+    float vT = powf(10.0f, (spl - g.spl_ref) / 10.0f) - kSpectralEps;
+    if (vT < 0.0f) vT = 0.0f;
+    float sn = 0.f, sth = 0.f;
+    for (int k = g.band_start[b] + lane; k < g.band_start[b + 1]; k += 32) {
+      sn += noise_t[ro + k];
+      sth += (spl >= __ldg(&g.abs_thr_spl[k])) ? vT : __ldg(&g.abs_thr_lin[k]);
+    }
+    sn = warp_sum(sn);
+    sth = warp_sum(sth);
+    if (lane == 0) {
+      float p = 0.f;
+      if (g.band_start[b + 1] > g.band_start[b]) {   // masking_veto.c:178-213
+        const float nmr = 10.0f * log10f((sn + kSpectralEps) / (sth + kSpectralEps));
+        if (nmr <= 0.0f) p = 1.0f;
+        else if (nmr >= kVetoNmrRange) p = 0.0f;
+        else p = 1.0f - (nmr / kVetoNmrRange);
+      }
+      band_p[(size_t)i * kBandPitch + b] = p;
+    }
+  }
+}
+
+// per-band protection EMA (spectral_smoother.c:213-223)
+__global__ void pscan_kernel(const GeoK g, int first_active, int active,
+                             float* __restrict__ band_p, float* __restrict__ p_state) {
+  const int b = threadIdx.x;
+  if (b >= g.nb) return;
+  float m = p_state[b];
+  for (int f = 0; f < active; f++) {
+    const size_t o = (size_t)(first_active + f) * kBandPitch + b;
+    m = (kVetoSmoothing * band_p[o]) + ((1.0f - kVetoSmoothing) * m);
+    band_p[o] = m;
+  }
+  p_state[b] = m;
+}
+
+// ---------------------------------------------------------------------------
+// (frame, bin): veto interpolation, Wiener gain, whitened floor, apply
+// ---------------------------------------------------------------------------
+struct FinalArgs {
+  int first_active, frames, mask_stride, wt_stride, use_veto, residual;
+  float depth, reduction, tonal, whitening;
+};
+
+__global__ void __launch_bounds__(256)
+final_kernel(const GeoK g, FinalArgs a, const float* __restrict__ Xre_t,
+             const float* __restrict__ Xim_t, const float* __restrict__ noise_t,
+             const float* __restrict__ Mg, const float* __restrict__ alpha,
+             const float* __restrict__ stable, const float* __restrict__ band_p,
+             const float* __restrict__ wt, const float* __restrict__ mask,
+             float* __restrict__ Yre, float* __restrict__ Yim) {
+  __shared__ float prot[kBandPitch];
+  const int i = blockIdx.y;
+  const bool active = i >= a.first_active;
+  if (active && a.use_veto) {
+    if (threadIdx.x < kBandPitch) {
+      const int b = threadIdx.x;
+      float v = 0.f;
+      if (b < g.nb) {
+        // spatial 3-tap from band 1 upwards (spectral_smoother.c:194-211)
+        const float* p = band_p + (size_t)i * kBandPitch;
+        const float cur = p[b];
+        if (b == 0 || g.nb < 2) v = cur;
+        else {
+          const float next = (b < g.nb - 1) ? p[b + 1] : cur;
+          v = (0.25f * p[b - 1]) + (0.5f * cur) + (0.25f * next);
+        }
+      }
+      prot[b] = v;
+    }
+    __syncthreads();
+  }
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.Kp) return;
+  const size_t o = (size_t)i * g.Kp + k;
+  const float xr = Xre_t[o], xi = Xim_t[o];
+  if (!active || k >= g.K) {
+    Yre[o] = xr;
+    Yim[o] = xi;
+    return;
+  }
+  const float n = noise_t[o];
+  const float spec = Mg[o];
+  float al = alpha[o];
+  if (a.use_veto) {
+    // masking_veto.c:230-266
+    const int cb = __ldg(&g.cband[k]);
+    float bp;
+    if (cb < g.nb - 1) {
+      const float x0 = g.centre[cb], x1 = g.centre[cb + 1];
+      const float y0 = prot[cb], y1 = prot[cb + 1];
+      if (x1 > x0) {
+        const float t = ((float)k - x0) / (x1 - x0);
+        const float tc = fmaxf(0.0f, fminf(1.0f, t));
+        bp = (y0 * (1.0f - tc)) + (y1 * tc);
+      } else {
+        bp = y0;
+      }
+    } else {
+      bp = prot[g.nb - 1];
+    }
+    const float bin_snr = stable[o] / (n + kSpectralEps);
+    const float sc = fminf(bin_snr / 1.0f, 1.0f);
+    const float veto = bp * sc * a.depth;
+    al = al + ((1.0f - al) * veto);
+  }
+  // gain_calculator.c:27-69
+  const float sn = n * al;
+  float gain;
+  if (sn > FLT_MIN) gain = (spec > sn) ? (spec - sn) / spec : 0.0f;
+  else gain = 1.0f;
+  // noise_floor_manager.c:94-157
+  if (a.reduction >= 0.999f && a.tonal >= 0.999f) {
+    gain = 1.0f;
+  } else {
+    float m = mask[(size_t)i * a.mask_stride + k];
+    if (m > 0.0f) m = sqrtf(sqrtf(m));
+    const float dual = (a.reduction * (1.0f - m)) + (a.tonal * m);
+    const float target = dual + (a.whitening * (a.reduction - dual));
+    const float rdepth = 1.0f - target;
+    const float eff = 1.0f + (rdepth * (wt[(size_t)i * a.wt_stride + k] - 1.0f));
+    float fl = target * eff;
+    if (fl > 1.0f) fl = 1.0f;
+    gain = fmaxf(fl, gain);
+  }
+  // denoiser_post_process.c:36-50
+  if (a.residual) {
+    Yre[o] = xr - (xr * gain);
+    Yim[o] = xi - (xi * gain);
+  } else {
+    Yre[o] = xr * gain;
+    Yim[o] = xi * gain;
+  }
+}
+
+}  // namespace
+
+bool launch_morph_profile(const GeoK& g, const float* prof, float aggressiveness, float* out,
+                          cudaStream_t st) {
+  morph_kernel<<<(g.Kp + 255) / 256, 256, 0, st>>>(g, prof, aggressiveness, out);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+bool launch_fill_rows(const GeoK& g, const float* row, float* dst, int rows, cudaStream_t st) {
+  if (rows <= 0) return true;
+  dim3 grid((g.Kp + 255) / 256, rows < 1024 ? rows : 1024);
+  fill_rows_kernel<<<grid, 256, 0, st>>>(g, row, dst, rows);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+bool launch_snr(const GeoK& g, const float* P, const float* noise, float* S, int frames,
+                cudaStream_t st) {
+  if (frames <= 0) return true;
+  dim3 grid((g.Kp + 255) / 256, frames);
+  snr_kernel<<<grid, 256, 0, st>>>(g, P, noise, S);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+bool launch_tonal_mask(const GeoK& g, const float* det, int det_stride, int rows, float* mask,
+                       cudaStream_t st) {
+  if (rows <= 0) return true;
+  const size_t smem = sizeof(float) * (size_t)(g.K + kTonalWindow);
+  if (smem > 48 * 1024)
+    SB_CUDA(cudaFuncSetAttribute((const void*)tonal_mask_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tonal_mask_kernel<<<rows, 256, smem, st>>>(g, det, det_stride, mask, g.Kp);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+bool launch_whitening(const GeoK& g, const float* noise, int noise_stride, int rows,
+                      float whitening, float* wt, cudaStream_t st) {
+  if (rows <= 0) return true;
+  int P2 = 1;
+  while (P2 < g.K) P2 <<= 1;
+  const size_t smem = sizeof(float) * (size_t)(P2 + g.K);
+  if (smem > 48 * 1024)
+    SB_CUDA(cudaFuncSetAttribute((const void*)whitening_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  whitening_kernel<<<rows, 512, smem, st>>>(g, noise, noise_stride, whitening, wt, g.Kp, P2);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+// Runs the whole chain for the frames of one sub-call.  Rows of the "delayed"
+// buffers (Xre/Xim/noise) are indexed by the frame index i of this call: in 2D
+// they carry 4 history rows in front, so row i IS frame i-4; in 1D row i is
+// frame i itself.
+bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cudaStream_t st) {
+  const int M = a.frames;
+  if (M <= 0) return true;
+  const int fa = a.first_active < M ? a.first_active : M;
+  const int active = M - fa;
+  const bool use_veto = !(a.depth < 0.0f);   // masking_veto.c:131-134
+  if (active > 0) {
+    PreArgs pa;
+    pa.first_active = fa;
+    pa.two_d = a.two_d ? 1 : 0;
+    pa.mask_stride = a.mask_stride;
+    pa.alpha_max_user = kAlphaMin + (a.strength * (kAlphaMax - kAlphaMin));
+    pa.tonal_gain = a.tonal;
+    dim3 grid((g.Kp + 255) / 256, active);
+    gain_pre_kernel<<<grid, 256, 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, L.mask, L.Mg,
+                                          L.alpha, L.stable);
+    SB_LAUNCH_CHECK();
+    if (use_veto || !a.two_d) {
+      bin_scan_kernel<<<(g.K + 127) / 128, 128, 0, st>>>(g, fa, active, a.two_d ? 1 : 0,
+                                                         a.smoothing, L.P, L.noise, L.Mg,
+                                                         L.stable, h.d_stable, h.d_sp_prev);
+      SB_LAUNCH_CHECK();
+    }
+    if (use_veto) {
+      band_kernel<<<active, 256, 0, st>>>(g, fa, a.two_d ? 1 : 0, L.stable, L.Xre, L.noise,
+                                          L.band_a);
+      SB_LAUNCH_CHECK();
+      tscan_kernel<<<1, kBandPitch, 0, st>>>(g, fa, active, L.band_a, L.band_T,
+                                             h.d_band_state);
+      SB_LAUNCH_CHECK();
+      nmr_kernel<<<active, 256, 0, st>>>(g, fa, L.band_T, L.noise, L.band_p);
+      SB_LAUNCH_CHECK();
+      pscan_kernel<<<1, kBandPitch, 0, st>>>(g, fa, active, L.band_p,
+                                             h.d_band_state + kBandPitch);
+      SB_LAUNCH_CHECK();
+    }
+  }
+  FinalArgs fa2;
+  fa2.first_active = fa;
+  fa2.frames = M;
+  fa2.mask_stride = a.mask_stride;
+  fa2.wt_stride = a.wt_stride;
+  fa2.use_veto = use_veto ? 1 : 0;
+  fa2.residual = a.residual ? 1 : 0;
+  fa2.depth = a.depth;
+  fa2.reduction = a.reduction;
+  fa2.tonal = a.tonal;
+  fa2.whitening = a.whitening;
+  dim3 grid((g.Kp + 255) / 256, M);
+  final_kernel<<<grid, 256, 0, st>>>(g, fa2, L.Xre, L.Xim, L.noise, L.Mg, L.alpha, L.stable,
+                                     L.band_p, L.wt, L.mask, L.Yre, L.Yim);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+}  // namespace sb

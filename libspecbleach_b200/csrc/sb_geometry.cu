@@ -1,0 +1,257 @@
+// Geometry tables: everything derived from (sample_rate, frame_ms) once, on the
+// host, and uploaded to the device.  Host arithmetic deliberately follows the
+// reference's float expressions so that integer sizes and table entries agree.
+#include "sb_engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace sb {
+
+static std::mutex g_geo_mu;
+static std::map<std::tuple<int, uint32_t, uint32_t>, Geometry*> g_geo_cache;
+
+template <typename T>
+static T* upload(Geometry* G, const std::vector<T>& v) {
+  T* d = nullptr;
+  if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
+  G->dev_allocs.push_back(d);
+  return d;
+}
+
+// Bark band upper edges in Hz (critical_bands.c:25-28)
+static const float kBark[25] = {100.f,  200.f,  300.f,  400.f,  510.f,  630.f,  770.f,
+                                920.f,  1080.f, 1270.f, 1480.f, 1720.f, 2000.f, 2320.f,
+                                2700.f, 3150.f, 3700.f, 4400.f, 5300.f, 6400.f, 7700.f,
+                                9500.f, 12000.f, 15500.f, 19000.f};
+
+static void factorize(int m, int* fac, int* nfac) {
+  int n = 0;
+  while (m % 4 == 0) { fac[n++] = 4; m /= 4; }
+  while (m % 2 == 0) { fac[n++] = 2; m /= 2; }
+  while (m % 5 == 0) { fac[n++] = 5; m /= 5; }
+  while (m % 3 == 0) { fac[n++] = 3; m /= 3; }
+  for (int p = 7; p * p <= m; p += 2)
+    while (m % p == 0) { fac[n++] = p; m /= p; }
+  if (m > 1) fac[n++] = m;
+  *nfac = n;
+}
+
+// spl_reference_value: absolute_hearing_thresholds.c:86-89,118-139.  The
+// reference takes the peak of a float FFT of a Vorbis-windowed 1 kHz sine; the
+// peak lies in the main lobe, so a double-precision DFT over the bins around it
+// gives the same maximum (to ~1e-7 relative).
+static float compute_spl_reference(uint32_t sr, int N) {
+  std::vector<float> x(N);
+  const float pi = 3.14159265358979323846f;
+  for (int k = 0; k < N; k++) {
+    float s = 1.f * sinf((2.f * pi * (float)k * 1000.f) / (float)sr);
+    float p = (float)k / (float)N;
+    float w = sinf(pi / 2.f * powf(sinf(pi * p), 2.f));   // spectral_utils.c:44-47
+    if (!isnormal(w)) w = 0.f;
+    x[k] = s * w;
+  }
+  int k0 = (int)lround(1000.0 * (double)N / (double)sr);
+  int lo = k0 - 24 < 0 ? 0 : k0 - 24;
+  int hi = k0 + 24 > N / 2 ? N / 2 : k0 + 24;
+  double best = 0.0;
+  for (int k = lo; k <= hi; k++) {
+    double re = 0.0, im = 0.0;
+    const double w = -2.0 * M_PI * (double)k / (double)N;
+    for (int n = 0; n < N; n++) {
+      double a = w * (double)n;
+      re += x[n] * cos(a);
+      im += x[n] * sin(a);
+    }
+    double p = (k == 0 || k == N / 2) ? re * re : re * re + im * im;
+    if (p > best) best = p;
+  }
+  return 90.f - (10.f * log10f((float)best + kSpectralEps));
+}
+
+const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  uint32_t ms_bits;
+  memcpy(&ms_bits, &frame_ms, 4);
+  std::lock_guard<std::mutex> lock(g_geo_mu);
+  auto key = std::make_tuple(dev, sample_rate, ms_bits);
+  auto it = g_geo_cache.find(key);
+  if (it != g_geo_cache.end()) return it->second;
+
+  Geometry* G = new Geometry();
+  G->sample_rate = sample_rate;
+  G->frame_ms = frame_ms;
+  GeoK& g = G->k;
+  memset(&g, 0, sizeof(g));
+  g.sr = (int)sample_rate;
+  // stft_processor.c:57-58,68 ; fft_transform.c:59,119-123
+  const uint32_t frame = (uint32_t)((frame_ms / 1000.f) * (float)sample_rate);
+  if (frame < 4) { delete G; return nullptr; }
+  uint32_t N = frame + kZeroPad;
+  N += (N & 1u);
+  g.frame = (int)frame;
+  g.N = (int)N;
+  g.hop = (int)(frame / kOverlap);
+  g.K = (int)(N / 2 + 1);
+  g.Kp = (g.K + 3) & ~3;
+  g.M = (int)(N / 2);
+  g.cp = (int)(N / 2 - frame / 2);
+  g.frame_p = (g.frame + 3) & ~3;
+  factorize(g.M, g.fac, &g.nfac);
+
+  // periodic Hann over `frame` (spectral_utils.c:34-37, general_utils.c:26-31)
+  const float pi = 3.14159265358979323846f;
+  std::vector<float> win(frame);
+  for (uint32_t k = 0; k < frame; k++) {
+    float p = (float)k / (float)frame;
+    float v = 0.5f - (0.5f * cosf(2.f * pi * p));
+    if (!isnormal(v)) v = 0.f;
+    win[k] = v;
+  }
+  // stft_windows.c:103-118
+  float sum = 0.f;
+  for (uint32_t k = 0; k < frame; k++) sum += win[k] * win[k];
+  g.scale = (sum < 1.1920929e-7f) ? 1.f : sum * ((float)N / (float)g.hop);
+
+  // FFT twiddles
+  std::vector<float2> tw(g.M), twn(g.M + 1);
+  for (int k = 0; k < g.M; k++) {
+    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.M;
+    tw[k] = make_float2((float)cosl(a), (float)sinl(a));
+  }
+  for (int k = 0; k <= g.M; k++) {
+    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.N;
+    twn[k] = make_float2((float)cosl(a), (float)sinl(a));
+  }
+
+  // Bark bands (critical_bands.c:96-116,138-149; quirk: bin edges use K as fft size)
+  const float nyq = (float)sample_rate / 2.f;
+  int last_valid = 0;
+  for (int i = 0; i < 25; i++)
+    if (kBark[i] < nyq) last_valid = i;
+  g.nb = last_valid + 1;
+  {
+    std::vector<uint32_t> delim(g.nb), nbins(g.nb);
+    for (int b = 0; b < g.nb; b++) {
+      uint32_t bin = (uint32_t)((kBark[b] / ((float)sample_rate / (float)g.K)) + 0.5f);
+      if (b == 0) { nbins[b] = bin; delim[b] = bin; }
+      else if (b == g.nb - 1) { delim[b] = (uint32_t)g.K; nbins[b] = delim[b] - delim[b - 1]; }
+      else { nbins[b] = bin - delim[b - 1]; delim[b] = bin; }
+    }
+    for (int b = 0; b < g.nb; b++) {
+      uint32_t start = delim[b] - nbins[b], end = delim[b];
+      if (end > (uint32_t)g.K) end = (uint32_t)g.K;        // defensive (tiny frames)
+      if (start > end) start = end;
+      g.band_start[b] = (int)start;
+      g.band_start[b + 1] = (int)end;
+      g.centre[b] = (float)start + ((float)(end - start) / 2.0f);   // masking_veto.c:103-110
+    }
+  }
+  // temporal masking decays (masking_estimator.c:146-160)
+  const float hop_time = (float)g.N / (4.0f * (float)sample_rate);
+  for (int b = 0; b < g.nb; b++) {
+    const float bark = fminf((float)b, 24.0f);
+    const float weight = bark / 24.0f;
+    const float tau = ((1.0f - weight) * 0.100f) + (weight * 0.025f);
+    const float fwd = expf(-hop_time / tau);
+    g.fwd_pow[b] = powf(fwd, kPowerLawExp);
+  }
+  g.bwd = expf(-hop_time / 0.010f);
+  g.spl_ref = compute_spl_reference(sample_rate, g.N);
+
+  // absolute threshold of hearing (absolute_hearing_thresholds.c:161-170, 141-159)
+  std::vector<float> thr_spl(g.Kp, 0.f), thr_lin(g.Kp, 0.f);
+  for (int k = 0; k < g.K; k++) {
+    const float freq = fmaxf((float)k * ((float)sample_rate / (float)g.N), 20.f);
+    const float fk = freq / 1000.f;
+    thr_spl[k] = (3.64f * powf(fk, -0.8f)) - (6.5f * expf(-0.6f * powf(fk - 3.3f, 2.f))) +
+                 (powf(10.f, -3.f) * powf(fk, 4.f));
+    float lin = powf(10.f, (thr_spl[k] - g.spl_ref) / 10.f) - kSpectralEps;
+    thr_lin[k] = lin < 0.f ? 0.f : lin;
+  }
+  std::vector<int> cband(g.Kp, 0), bob(g.Kp, 0);
+  {
+    int cur = 0;
+    for (int k = 0; k < g.K; k++) {   // masking_veto.c:233-236
+      while (cur < g.nb - 1 && (float)k > g.centre[cur + 1]) cur++;
+      cband[k] = cur;
+    }
+    for (int b = 0; b < g.nb; b++)
+      for (int k = g.band_start[b]; k < g.band_start[b + 1]; k++) bob[k] = b;
+  }
+
+  g.win = upload(G, win);
+  g.tw = upload(G, tw);
+  g.twn = upload(G, twn);
+  g.abs_thr_spl = upload(G, thr_spl);
+  g.abs_thr_lin = upload(G, thr_lin);
+  g.cband = upload(G, cband);
+  g.band_of_bin = upload(G, bob);
+  if (!g.win || !g.tw || !g.twn || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
+      !g.band_of_bin) {
+    set_error("geometry upload", cudaGetLastError(), __FILE__, __LINE__);
+    for (void* p : G->dev_allocs) cudaFree(p);
+    delete G;
+    return nullptr;
+  }
+  g_geo_cache[key] = G;
+  return G;
+}
+
+}  // namespace sb
+
+namespace sb {
+
+// Geometry for the FFT-only debug entry point: frame == N, no padding, unit window.
+Geometry* make_fft_geometry(int fft_size) {
+  if (fft_size < 4 || (fft_size & 1)) return nullptr;
+  Geometry* G = new Geometry();
+  GeoK& g = G->k;
+  memset(&g, 0, sizeof(g));
+  g.sr = 48000;
+  g.frame = fft_size;
+  g.N = fft_size;
+  g.hop = fft_size;
+  g.K = fft_size / 2 + 1;
+  g.Kp = (g.K + 3) & ~3;
+  g.M = fft_size / 2;
+  g.cp = 0;
+  g.frame_p = (g.frame + 3) & ~3;
+  g.scale = 1.0f;
+  factorize(g.M, g.fac, &g.nfac);
+  std::vector<float> win(fft_size, 1.0f);
+  std::vector<float2> tw(g.M), twn(g.M + 1);
+  for (int k = 0; k < g.M; k++) {
+    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.M;
+    tw[k] = make_float2((float)cosl(a), (float)sinl(a));
+  }
+  for (int k = 0; k <= g.M; k++) {
+    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.N;
+    twn[k] = make_float2((float)cosl(a), (float)sinl(a));
+  }
+  g.win = upload(G, win);
+  g.tw = upload(G, tw);
+  g.twn = upload(G, twn);
+  if (!g.win || !g.tw || !g.twn) {
+    free_geometry(G);
+    return nullptr;
+  }
+  return G;
+}
+
+void free_geometry(Geometry* G) {
+  if (!G) return;
+  for (void* p : G->dev_allocs) cudaFree(p);
+  delete G;
+}
+
+}  // namespace sb

@@ -1,0 +1,260 @@
+// STFT kernels: framing + Hann + centred zero-pad + real FFT (forward), the
+// inverse real FFT + synthesis window, and the ordered overlap-add.
+//
+// Replaces, for a whole batch of frames at once, the per-hop loop of
+//   stft_processor.c:126-175   (FIFO, analysis, synthesis, OLA)
+//   fft_transform.c:165-221    (centred load/crop, FFTW R2HC / HC2R)
+//   stft_windows.c:103-139     (window and 1/scale)
+//   spectral_features.c:80-107 (power spectrum)
+//
+// FFT: one CTA per frame.  The N real samples are packed into M = N/2 complex
+// points, transformed by a mixed-radix Stockham autosort FFT that ping-pongs
+// between two shared-memory buffers (radix 4 and 2 hard-wired, any other prime
+// factor through a generic O(r) per output butterfly), and split into the
+// N/2+1 bins of the real transform.  The frame sizes of the library are not
+// powers of two (N = frame + 800), hence the runtime factor list.
+#include "sb_common.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int kFftThreads = 256;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// Mixed-radix Stockham DIF passes over M complex points held in shared memory.
+// Returns the buffer that holds the result.  INV conjugates every twiddle.
+template <bool INV>
+__device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
+  const int M = g.M;
+  const float2* __restrict__ tw = g.tw;
+  int len = M;
+  int s = 1;
+  for (int f = 0; f < g.nfac; f++) {
+    const int r = g.fac[f];
+    const int l = len / r;
+    const int tstep = M / len;
+    if (r == 4) {
+      for (int idx = threadIdx.x; idx < M / 4; idx += blockDim.x) {
+        const int j = idx / s;
+        const int q = idx - j * s;
+        const float2 a = x[q + s * j];
+        const float2 b = x[q + s * (j + l)];
+        const float2 c = x[q + s * (j + 2 * l)];
+        const float2 d = x[q + s * (j + 3 * l)];
+        const float2 apc = cadd(a, c), amc = csub(a, c);
+        const float2 bpd = cadd(b, d), bmd = csub(b, d);
+        // forward: -i*(b-d); inverse: +i*(b-d)
+        const float2 jb = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);
+        float2 w1 = __ldg(&tw[j * tstep]);
+        float2 w2 = __ldg(&tw[2 * j * tstep]);
+        float2 w3 = __ldg(&tw[3 * j * tstep]);
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        float2* o = &y[q + s * (4 * j)];
+        o[0] = cadd(apc, bpd);
+        o[s] = cmul(cadd(amc, jb), w1);
+        o[2 * s] = cmul(csub(apc, bpd), w2);
+        o[3 * s] = cmul(csub(amc, jb), w3);
+      }
+    } else if (r == 2) {
+      for (int idx = threadIdx.x; idx < M / 2; idx += blockDim.x) {
+        const int j = idx / s;
+        const int q = idx - j * s;
+        const float2 a = x[q + s * j];
+        const float2 b = x[q + s * (j + l)];
+        float2 w1 = __ldg(&tw[j * tstep]);
+        if (INV) w1.y = -w1.y;
+        y[q + s * (2 * j)] = cadd(a, b);
+        y[q + s * (2 * j + 1)] = cmul(csub(a, b), w1);
+      }
+    } else {
+      // generic radix: one work item per output point
+      const int rstep = M / r;
+      for (int item = threadIdx.x; item < M; item += blockDim.x) {
+        const int idx = item / r;        // butterfly
+        const int t = item - idx * r;    // output index inside the butterfly
+        const int j = idx / s;
+        const int q = idx - j * s;
+        float2 acc = x[q + s * j];
+        int ut = 0;
+        for (int u = 1; u < r; u++) {
+          ut += t;
+          if (ut >= r) ut -= r;
+          float2 w = __ldg(&tw[ut * rstep]);
+          if (INV) w.y = -w.y;
+          const float2 v = x[q + s * (j + u * l)];
+          acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+          acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+        }
+        float2 wo = __ldg(&tw[j * t * tstep]);
+        if (INV) wo.y = -wo.y;
+        y[q + s * (r * j + t)] = cmul(acc, wo);
+      }
+    }
+    __syncthreads();
+    float2* tmp = x; x = y; y = tmp;
+    len = l;
+    s *= r;
+  }
+  return x;
+}
+
+// ---------------------------------------------------------------------------
+// forward: frame f = xbuf[f*hop, f*hop+frame) -> Hann -> centre in N -> rFFT
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFftThreads)
+forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__ Xre,
+               float* __restrict__ Xim, float* __restrict__ P) {
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + g.M;
+  const int f = blockIdx.x;
+  const float* __restrict__ src = xbuf + (size_t)f * g.hop;
+  const float* __restrict__ win = g.win;
+  // fft_load_input_samples + INPUT window (fft_transform.c:165-182, stft_windows.c:120-127)
+  for (int k = threadIdx.x; k < g.M; k += blockDim.x) {
+    const int i0 = 2 * k - g.cp;
+    const int i1 = i0 + 1;
+    float v0 = 0.f, v1 = 0.f;
+    if (i0 >= 0 && i0 < g.frame) v0 = src[i0] * __ldg(&win[i0]);
+    if (i1 >= 0 && i1 < g.frame) v1 = src[i1] * __ldg(&win[i1]);
+    a[k] = make_float2(v0, v1);
+  }
+  __syncthreads();
+  const float2* Z = stockham<false>(a, b, g);
+  // split into the real spectrum; halfcomplex bin k <-> (Xre[k], Xim[k])
+  float* __restrict__ re = Xre + (size_t)f * g.Kp;
+  float* __restrict__ im = Xim + (size_t)f * g.Kp;
+  float* __restrict__ pw = P + (size_t)f * g.Kp;
+  const int M = g.M;
+  for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
+    float xr = 0.f, xi = 0.f;
+    if (k == 0) {
+      xr = Z[0].x + Z[0].y;
+    } else if (k == M) {
+      xr = Z[0].x - Z[0].y;
+    } else if (k < M) {
+      const float2 z1 = Z[k];
+      const float2 z2 = Z[M - k];
+      const float er = 0.5f * (z1.x + z2.x), ei = 0.5f * (z1.y - z2.y);
+      const float dr = 0.5f * (z1.x - z2.x), di = 0.5f * (z1.y + z2.y);
+      // O = D / i = (di, -dr);  X = E + w_N^k * O
+      const float2 w = __ldg(&g.twn[k]);
+      xr = er + (di * w.x + dr * w.y);
+      xi = ei + (di * w.y - dr * w.x);
+    }
+    re[k] = xr;
+    im[k] = xi;
+    // spectral_features.c:80-107 (DC and Nyquist have xi == 0 exactly)
+    pw[k] = fmaf(xr, xr, xi * xi);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// inverse: Y -> unnormalised HC2R -> OUTPUT window / scale -> centre crop
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFftThreads)
+inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restrict__ Yim,
+               float* __restrict__ synth) {
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + g.M;
+  const int f = blockIdx.x;
+  const int M = g.M;
+  const float* __restrict__ re = Yre + (size_t)f * g.Kp;
+  const float* __restrict__ im = Yim + (size_t)f * g.Kp;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    float xr = re[k], xi = (k == 0) ? 0.f : im[k];
+    float yr = re[M - k], yi = (k == 0) ? 0.f : -im[M - k];   // conj X[M-k]
+    const float er = xr + yr, ei = xi + yi;
+    const float dr = xr - yr, di = xi - yi;
+    const float2 w = __ldg(&g.twn[k]);
+    // t = conj(w) * D ; Z = E + i*t
+    const float tr = dr * w.x + di * w.y;
+    const float ti = di * w.x - dr * w.y;
+    a[k] = make_float2(er - ti, ei + tr);
+  }
+  __syncthreads();
+  const float2* z = stockham<true>(a, b, g);
+  // OUTPUT window then divide by scale (stft_windows.c:120-137), crop (fft_transform.c:184-201)
+  float* __restrict__ out = synth + (size_t)f * g.frame_p;
+  const float* __restrict__ win = g.win;
+  const float* zf = reinterpret_cast<const float*>(z);
+  for (int i = threadIdx.x; i < g.frame; i += blockDim.x) {
+    const float v = zf[g.cp + i];
+    out[i] = (v * __ldg(&win[i])) / g.scale;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// overlap-add, in the reference's summation order (stft_processor.c:162-170):
+// the accumulator receives frames oldest first.  i runs over the n output
+// samples of this call followed by the `frame` samples of the new tail.
+// ---------------------------------------------------------------------------
+__global__ void ola_kernel(const GeoK g, const float* __restrict__ synth, int frames,
+                           int carry, unsigned n, const float* __restrict__ tail_in,
+                           float* __restrict__ tail_out, float* __restrict__ y) {
+  const unsigned total = n + (unsigned)g.frame;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += gridDim.x * blockDim.x) {
+    float acc = (i < (unsigned)g.frame) ? tail_in[i] : 0.f;
+    const long long ic = (long long)i + carry;
+    long long fmax = ic / g.hop - 1;
+    if (fmax > frames - 1) fmax = frames - 1;
+    long long lo = ic - g.frame + 1;
+    long long fmin = lo <= 0 ? 0 : (lo + g.hop - 1) / g.hop - 1;
+    if (fmin < 0) fmin = 0;
+    for (long long f = fmin; f <= fmax; f++) {
+      const long long o = (f + 1) * g.hop - carry;   // first output sample of frame f
+      acc += synth[(size_t)f * g.frame_p + (size_t)(i - o)];
+    }
+    if (i < n) y[i] = acc;
+    else tail_out[i - n] = acc;
+  }
+}
+
+}  // namespace
+
+static bool set_fft_smem(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  return true;
+}
+
+bool launch_forward(const GeoK& g, const float* xbuf, int frames, float* Xre, float* Xim,
+                    float* P, cudaStream_t st) {
+  if (frames <= 0) return true;
+  const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
+  if (!set_fft_smem((const void*)forward_kernel, smem)) return false;
+  forward_kernel<<<frames, kFftThreads, smem, st>>>(g, xbuf, Xre, Xim, P);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+bool launch_inverse(const GeoK& g, const float* Yre, const float* Yim, int frames,
+                    float* synth, cudaStream_t st) {
+  if (frames <= 0) return true;
+  const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
+  if (!set_fft_smem((const void*)inverse_kernel, smem)) return false;
+  inverse_kernel<<<frames, kFftThreads, smem, st>>>(g, Yre, Yim, frames ? synth : synth);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+bool launch_ola(const GeoK& g, const float* synth, int frames, uint32_t carry, uint32_t n,
+                const float* tail_in, float* tail_out, float* y, cudaStream_t st) {
+  const unsigned total = n + (unsigned)g.frame;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ola_kernel<<<blocks, 256, 0, st>>>(g, synth, frames, (int)carry, n, tail_in, tail_out, y);
+  SB_LAUNCH_CHECK();
+  return true;
+}
+
+}  // namespace sb
