@@ -79,6 +79,11 @@ bool specbleach_b200_stats_get(SpecbleachB200Stats* out);
 bool specbleach_b200_get_geometry(SpectralBleachHandle instance, uint32_t* frame,
                                   uint32_t* fft_size, uint32_t* hop, uint32_t* bins);
 
+/* FFMA micro-benchmark on the current device: sustained FP32 TFLOP/s (FMA = 2
+ * FLOP).  It is the denominator of the NLM kernel's roofline, which is bound by
+ * the FP32 pipe and not by HBM (MEASURED_PEAKS.json has no FP32 figure). */
+double specbleach_b200_debug_fp32_peak_tflops(void);
+
 /* Single-kernel entry points used by the parity tests (host buffers). ------ */
 /* NLM over a whole SNR map snr[frames][bins] (row-major, pitch = bins):
  * out[j] = filtered frame j-4 as the reference returns it after pushing frame

@@ -63,7 +63,7 @@ PUBLIC_SYMBOLS = [pre + n for pre in ("specbleach_", "specbleach_2d_") for n in 
 EXTENSION_SYMBOLS = ["specbleach_b200_" + n for n in (
     "device_count", "set_device", "last_error", "host_alloc", "host_free", "configure",
     "process_device", "process_batch", "process_batch_device", "profile", "stats_reset",
-    "stats_get", "get_geometry", "debug_nlm", "debug_rfft")]
+    "stats_get", "get_geometry", "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft")]
 
 
 def lib():
@@ -125,6 +125,7 @@ def lib():
     L.specbleach_b200_stats_get.argtypes = [C.POINTER(Stats)]
     L.specbleach_b200_get_geometry.restype = C.c_bool
     L.specbleach_b200_get_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
+    L.specbleach_b200_debug_fp32_peak_tflops.restype = C.c_double
     L.specbleach_b200_debug_nlm.restype = C.c_bool
     L.specbleach_b200_debug_nlm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float,
                                             C.c_void_p]

@@ -251,6 +251,55 @@ bool specbleach_b200_get_geometry(SpectralBleachHandle instance, uint32_t* frame
   return true;
 }
 
+// ---- FP32-pipe peak: FFMA micro-benchmark (denominator of the NLM roofline) ----
+}  // extern "C" (kernel below has C++ linkage)
+
+namespace {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = fmaf(v[i], a, b);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += v[i];
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true: keeps the loop alive
+}
+}  // namespace
+
+extern "C" {
+
+double specbleach_b200_debug_fp32_peak_tflops(void) {
+  float* d = nullptr;
+  const int blocks = 148 * 8, threads = 256, iters = 4096;
+  if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, 0);
+    ffma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
 // ---- single-kernel entry points for the parity tests ----
 bool specbleach_b200_debug_nlm(const float* snr, uint32_t frames, uint32_t bins, float h,
                                float* out) {

@@ -184,6 +184,11 @@ struct Handle {
   float* d_stable = nullptr;      // [Kp]
   float* d_sp_prev = nullptr;     // [Kp] 1D release smoother
   float* d_band_state = nullptr;  // [2][32]: u = T_prev^0.6, protection memory
+  // static-noise caches: tonal mask and whitening weights of the manual profile
+  float* d_aux_mask = nullptr;    // [Kp]
+  float* d_aux_wt = nullptr;      // [Kp]
+  uint64_t aux_mask_version = 0, aux_wt_version = 0;
+  float aux_wt_whitening = -1.0f;
   // noise for the current call
   float* d_noise_cur = nullptr;   // [Kp]
   float* d_floor = nullptr;       // [Kp] manual floor (adaptive mode)
@@ -249,6 +254,8 @@ struct GainArgs {
   bool residual;
   int mask_stride;   // 0: one tonal mask row shared by all frames, else Kp
   int wt_stride;     // 0: one whitening-weight row shared by all frames, else Kp
+  const float* mask; // tonal mask rows (indexed by frame index * mask_stride)
+  const float* wt;   // whitening weight rows
 };
 bool launch_morph_profile(const GeoK& g, const float* prof, float aggressiveness, float* out,
                           cudaStream_t st);

@@ -69,7 +69,10 @@ static void lane_free(Lane& L) {
 
 // Sizes the scratch of a lane for sub-calls of up to F frames of geometry g.
 static bool lane_ensure(Lane& L, const GeoK& g, int F) {
-  if (!L.stream) SB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+  // Blocking streams on purpose: an event recorded on the legacy default stream
+  // (what torch.cuda.Event uses) then brackets the work of every lane, while
+  // lanes still overlap with each other.
+  if (!L.stream) SB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamDefault));
   const size_t samples = (size_t)g.frame + (size_t)(F + 1) * g.hop;
   if (L.cap_frames >= F && L.cap_Kp >= g.Kp && L.cap_frame_p >= g.frame_p &&
       L.cap_samples >= samples)
@@ -130,7 +133,8 @@ Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms) {
             dev_zalloc(&h->d_tail[0], g.frame) && dev_zalloc(&h->d_tail[1], g.frame) &&
             dev_zalloc(&h->d_stable, Kp) && dev_zalloc(&h->d_sp_prev, Kp) &&
             dev_zalloc(&h->d_band_state, 2 * kBandPitch) && dev_zalloc(&h->d_noise_cur, Kp) &&
-            dev_zalloc(&h->d_floor, Kp);
+            dev_zalloc(&h->d_floor, Kp) && dev_zalloc(&h->d_aux_mask, Kp) &&
+            dev_zalloc(&h->d_aux_wt, Kp);
   if (ok && two_d) {
     ok = dev_zalloc(&h->d_X_hist_re, 4 * Kp) && dev_zalloc(&h->d_X_hist_im, 4 * Kp) &&
          dev_zalloc(&h->d_noise_hist, 4 * Kp) && dev_zalloc(&h->d_S_hist, kSnrHist * Kp);
@@ -148,7 +152,8 @@ void handle_destroy(Handle* h) {
   cudaDeviceSynchronize();
   float* bufs[] = {h->d_prof, h->d_med_ring, h->d_hist, h->d_tail[0], h->d_tail[1],
                    h->d_X_hist_re, h->d_X_hist_im, h->d_noise_hist, h->d_S_hist, h->d_stable,
-                   h->d_sp_prev, h->d_band_state, h->d_noise_cur, h->d_floor, h->d_est};
+                   h->d_sp_prev, h->d_band_state, h->d_noise_cur, h->d_floor, h->d_est,
+                   h->d_aux_mask, h->d_aux_wt};
   for (float* b : bufs)
     if (b) cudaFree(b);
   delete h;
@@ -349,6 +354,8 @@ static bool denoise_frames(Handle* h, Lane& L, int M) {
   ga.residual = p.residual_listen;
   ga.mask_stride = 0;
   ga.wt_stride = 0;
+  ga.mask = h->d_aux_mask;
+  ga.wt = h->d_aux_wt;
   if (active > 0) {
     bool noise_static = !adaptive;
     if (noise_static && two_d && first_active < kDelayFrames) {
@@ -356,26 +363,34 @@ static bool denoise_frames(Handle* h, Lane& L, int M) {
         if (h->noise_hist_version[r] != h->noise_version) noise_static = false;
     }
     const bool transparent = (p.reduction >= 0.999f && p.tonal >= 0.999f);
-    const bool need_mask = !transparent || !(p.tonal >= 0.999f);
-    if (need_mask) {
-      if (h->profile_learned) {          // detection profile = MAX profile (tonal_detector.c:35-44)
-        if (!launch_tonal_mask(g, h->d_prof + 2 * Kp, 0, 1, L.mask, st)) return false;
-      } else if (noise_static) {
-        if (!launch_tonal_mask(g, h->d_noise_cur, 0, 1, L.mask, st)) return false;
+    if (!transparent) {
+      // tonal mask: detection profile = MAX profile once a median exists
+      // (tonal_detector.c:35-44), otherwise the (delayed) noise spectrum
+      if (h->profile_learned || noise_static) {
+        if (h->aux_mask_version != h->noise_version) {
+          const float* det = h->profile_learned ? h->d_prof + 2 * Kp : h->d_noise_cur;
+          if (!launch_tonal_mask(g, det, 0, 1, h->d_aux_mask, st)) return false;
+          h->aux_mask_version = h->noise_version;
+        }
       } else {
         if (!launch_tonal_mask(g, L.noise + (size_t)first_active * Kp, g.Kp, active,
                                L.mask + (size_t)first_active * Kp, st))
           return false;
+        ga.mask = L.mask;
         ga.mask_stride = g.Kp;
       }
-    }
-    if (!transparent) {
       if (noise_static) {
-        if (!launch_whitening(g, h->d_noise_cur, 0, 1, p.whitening, L.wt, st)) return false;
+        if (h->aux_wt_version != h->noise_version || h->aux_wt_whitening != p.whitening) {
+          if (!launch_whitening(g, h->d_noise_cur, 0, 1, p.whitening, h->d_aux_wt, st))
+            return false;
+          h->aux_wt_version = h->noise_version;
+          h->aux_wt_whitening = p.whitening;
+        }
       } else {
         if (!launch_whitening(g, L.noise + (size_t)first_active * Kp, g.Kp, active, p.whitening,
                               L.wt + (size_t)first_active * Kp, st))
           return false;
+        ga.wt = L.wt;
         ga.wt_stride = g.Kp;
       }
     }

@@ -69,43 +69,46 @@ __global__ void snr_kernel(const GeoK g, const float* __restrict__ P,
 }
 
 // 51-bin edge-clamped median over frequency, then the tonal mask.
+// grid = (bin tiles of 256, rows); each CTA stages its bins plus a 25-bin halo.
 __global__ void __launch_bounds__(256)
 tonal_mask_kernel(const GeoK g, const float* __restrict__ det, int det_stride,
                   float* __restrict__ mask, int mask_stride) {
-  extern __shared__ float sm[];
-  const int row = blockIdx.x;
+  __shared__ float sm[256 + kTonalWindow];
+  const int row = blockIdx.y;
   const float* __restrict__ d = det + (size_t)row * det_stride;
   const int half = kTonalWindow / 2;
   const int K = g.K;
-  for (int e = threadIdx.x; e < K + 2 * half; e += blockDim.x) {
-    int idx = e - half;
+  const int k0 = blockIdx.x * 256;
+  for (int e = threadIdx.x; e < 256 + 2 * half; e += blockDim.x) {
+    int idx = k0 + e - half;
     idx = idx < 0 ? 0 : (idx > K - 1 ? K - 1 : idx);
     sm[e] = d[idx];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
-    float m = 0.f;
-    if (k < K) {
-      const float* w = &sm[k];   // window = w[0..50]
-      float med = w[half];
-      for (int i = 0; i < kTonalWindow; i++) {
-        const float v = w[i];
-        int less = 0, leq = 0;
-        for (int j = 0; j < kTonalWindow; j++) {
-          const float u = w[j];
-          less += (u < v);
-          leq += (u <= v);
-        }
-        if (less <= half && half < leq) { med = v; break; }
+  const int k = k0 + threadIdx.x;
+  if (k >= g.Kp) return;
+  float m = 0.f;
+  if (k < K) {
+    const float* w = &sm[threadIdx.x];   // window = w[0..50]
+    float med = w[half];
+    for (int i = 0; i < kTonalWindow; i++) {
+      const float v = w[i];
+      int less = 0, leq = 0;
+#pragma unroll
+      for (int j = 0; j < kTonalWindow; j++) {
+        const float u = w[j];
+        less += (u < v);
+        leq += (u <= v);
       }
-      const float peak = w[half];
-      if (!(peak - med < kMinPeakProminence)) {
-        const float ratio = peak / (med + 1e-20f);
-        if (ratio > kPeakThreshold) m = (peak - med) / (peak + 1e-20f);
-      }
+      if (less <= half && half < leq) { med = v; break; }
     }
-    mask[(size_t)row * mask_stride + k] = m;
+    const float peak = w[half];
+    if (!(peak - med < kMinPeakProminence)) {
+      const float ratio = peak / (med + 1e-20f);
+      if (ratio > kPeakThreshold) m = (peak - med) / (peak + 1e-20f);
+    }
   }
+  mask[(size_t)row * mask_stride + k] = m;
 }
 
 // Whitening weights: smooth3(noise) -> median (bitonic sort) -> power-law weights.
@@ -210,6 +213,8 @@ __global__ void gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict
 // per-bin scans over frames: (1D) release smoothing, then the stabilised
 // clean-signal EMA of the veto (masking_veto.c:137-147)
 // ---------------------------------------------------------------------------
+constexpr int kScanBatch = 16;   // independent loads kept in flight per thread
+
 __global__ void bin_scan_kernel(const GeoK g, int first_active, int active, int two_d,
                                 float smoothing, const float* __restrict__ P,
                                 const float* __restrict__ noise_t, float* __restrict__ Mg,
@@ -217,38 +222,49 @@ __global__ void bin_scan_kernel(const GeoK g, int first_active, int active, int 
                                 float* __restrict__ sp_state) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= g.K) return;
+  const size_t Kp = g.Kp;
   float st = st_state[k];
+  size_t o = (size_t)first_active * Kp + k;
   if (two_d) {
-    size_t o = (size_t)first_active * g.Kp + k;
-    int f = 0;
-    for (; f + 4 <= active; f += 4) {
-      const float c0 = stable[o], c1 = stable[o + g.Kp], c2 = stable[o + 2 * (size_t)g.Kp],
-                  c3 = stable[o + 3 * (size_t)g.Kp];
-      st = (kVetoSmoothing * c0) + ((1.0f - kVetoSmoothing) * st); stable[o] = st;
-      st = (kVetoSmoothing * c1) + ((1.0f - kVetoSmoothing) * st); stable[o + g.Kp] = st;
-      st = (kVetoSmoothing * c2) + ((1.0f - kVetoSmoothing) * st); stable[o + 2 * (size_t)g.Kp] = st;
-      st = (kVetoSmoothing * c3) + ((1.0f - kVetoSmoothing) * st); stable[o + 3 * (size_t)g.Kp] = st;
-      o += 4 * (size_t)g.Kp;
-    }
-    for (; f < active; f++) {
-      st = (kVetoSmoothing * stable[o]) + ((1.0f - kVetoSmoothing) * st);
-      stable[o] = st;
-      o += g.Kp;
+    // the loads do not depend on the recurrence: fetch a batch, then chain the FMAs
+    for (int f = 0; f < active; f += kScanBatch) {
+      float c[kScanBatch];
+#pragma unroll
+      for (int i = 0; i < kScanBatch; i++)
+        c[i] = (f + i < active) ? stable[o + (size_t)i * Kp] : 0.f;
+#pragma unroll
+      for (int i = 0; i < kScanBatch; i++) {
+        if (f + i < active) {
+          st = (kVetoSmoothing * c[i]) + ((1.0f - kVetoSmoothing) * st);
+          stable[o + (size_t)i * Kp] = st;
+        }
+      }
+      o += (size_t)kScanBatch * Kp;
     }
   } else {
     float sp = sp_state[k];
-    size_t o = (size_t)first_active * g.Kp + k;
-    for (int f = 0; f < active; f++) {
-      const float cur = P[o];
-      // spectral_smoother.c:183-192 (release-only smoothing), state update :132-133
-      float v = cur;
-      if (cur > sp) v = (smoothing * sp) + ((1.0f - smoothing) * cur);
-      sp = v;
-      Mg[o] = v;
-      const float c = fmaxf(v - noise_t[o], 0.0f);
-      st = (kVetoSmoothing * c) + ((1.0f - kVetoSmoothing) * st);
-      stable[o] = st;
-      o += g.Kp;
+    for (int f = 0; f < active; f += kScanBatch) {
+      float c[kScanBatch], n[kScanBatch];
+#pragma unroll
+      for (int i = 0; i < kScanBatch; i++) {
+        const bool in = f + i < active;
+        c[i] = in ? P[o + (size_t)i * Kp] : 0.f;
+        n[i] = in ? noise_t[o + (size_t)i * Kp] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kScanBatch; i++) {
+        if (f + i < active) {
+          // spectral_smoother.c:183-192 (release-only smoothing), state update :132-133
+          float v = c[i];
+          if (c[i] > sp) v = (smoothing * sp) + ((1.0f - smoothing) * c[i]);
+          sp = v;
+          Mg[o + (size_t)i * Kp] = v;
+          const float cl = fmaxf(v - n[i], 0.0f);
+          st = (kVetoSmoothing * cl) + ((1.0f - kVetoSmoothing) * st);
+          stable[o + (size_t)i * Kp] = st;
+        }
+      }
+      o += (size_t)kScanBatch * Kp;
     }
     sp_state[k] = sp;
   }
@@ -345,16 +361,26 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
 // per-band forward-masking recursion, linear in u = T^0.6:
 //   T = (T_f^p + (T_prev*fwd)^p + (T_fut*bwd)^p)^(1/p)   (masking_estimator.c:270-288)
 __global__ void tscan_kernel(const GeoK g, int first_active, int active,
-                             const float* __restrict__ band_a, float* __restrict__ band_T,
+                             const float* __restrict__ band_a, float* __restrict__ band_u,
                              float* __restrict__ u_state) {
   const int b = threadIdx.x;
   if (b >= g.nb) return;
   float u = u_state[b];
   const float c = g.fwd_pow[b];
-  for (int f = 0; f < active; f++) {
-    const size_t o = (size_t)(first_active + f) * kBandPitch + b;
-    u = fmaf(c, u, band_a[o]);
-    band_T[o] = powf(u, kInvPower);
+  size_t o = (size_t)first_active * kBandPitch + b;
+  for (int f = 0; f < active; f += kScanBatch) {
+    float v[kScanBatch];
+#pragma unroll
+    for (int i = 0; i < kScanBatch; i++)
+      v[i] = (f + i < active) ? band_a[o + (size_t)i * kBandPitch] : 0.f;
+#pragma unroll
+    for (int i = 0; i < kScanBatch; i++) {
+      if (f + i < active) {
+        u = fmaf(c, u, v[i]);
+        band_u[o + (size_t)i * kBandPitch] = u;   // T = u^(1/0.6) is taken in nmr_kernel
+      }
+    }
+    o += (size_t)kScanBatch * kBandPitch;
   }
   u_state[b] = u;
 }
@@ -367,7 +393,7 @@ nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
   const size_t ro = (size_t)i * g.Kp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int b = warp; b < g.nb; b += nw) {
-    const float T = band_T[(size_t)i * kBandPitch + b];
+    const float T = powf(band_T[(size_t)i * kBandPitch + b], kInvPower);   // band_T holds u = T^0.6
     // absolute_hearing_thresholds.c:141-159
     const float spl = (10.0f * log10f(T + kSpectralEps)) + g.spl_ref;
     float vT = powf(10.0f, (spl - g.spl_ref) / 10.0f) - kSpectralEps;
@@ -398,10 +424,20 @@ __global__ void pscan_kernel(const GeoK g, int first_active, int active,
   const int b = threadIdx.x;
   if (b >= g.nb) return;
   float m = p_state[b];
-  for (int f = 0; f < active; f++) {
-    const size_t o = (size_t)(first_active + f) * kBandPitch + b;
-    m = (kVetoSmoothing * band_p[o]) + ((1.0f - kVetoSmoothing) * m);
-    band_p[o] = m;
+  size_t o = (size_t)first_active * kBandPitch + b;
+  for (int f = 0; f < active; f += kScanBatch) {
+    float v[kScanBatch];
+#pragma unroll
+    for (int i = 0; i < kScanBatch; i++)
+      v[i] = (f + i < active) ? band_p[o + (size_t)i * kBandPitch] : 0.f;
+#pragma unroll
+    for (int i = 0; i < kScanBatch; i++) {
+      if (f + i < active) {
+        m = (kVetoSmoothing * v[i]) + ((1.0f - kVetoSmoothing) * m);
+        band_p[o + (size_t)i * kBandPitch] = m;
+      }
+    }
+    o += (size_t)kScanBatch * kBandPitch;
   }
   p_state[b] = m;
 }
@@ -534,11 +570,8 @@ bool launch_snr(const GeoK& g, const float* P, const float* noise, float* S, int
 bool launch_tonal_mask(const GeoK& g, const float* det, int det_stride, int rows, float* mask,
                        cudaStream_t st) {
   if (rows <= 0) return true;
-  const size_t smem = sizeof(float) * (size_t)(g.K + kTonalWindow);
-  if (smem > 48 * 1024)
-    SB_CUDA(cudaFuncSetAttribute((const void*)tonal_mask_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tonal_mask_kernel<<<rows, 256, smem, st>>>(g, det, det_stride, mask, g.Kp);
+  dim3 grid((g.Kp + 255) / 256, rows);
+  tonal_mask_kernel<<<grid, 256, 0, st>>>(g, det, det_stride, mask, g.Kp);
   SB_LAUNCH_CHECK();
   return true;
 }
@@ -575,7 +608,7 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
     pa.alpha_max_user = kAlphaMin + (a.strength * (kAlphaMax - kAlphaMin));
     pa.tonal_gain = a.tonal;
     dim3 grid((g.Kp + 255) / 256, active);
-    gain_pre_kernel<<<grid, 256, 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, L.mask, L.Mg,
+    gain_pre_kernel<<<grid, 256, 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, a.mask, L.Mg,
                                           L.alpha, L.stable);
     SB_LAUNCH_CHECK();
     if (use_veto || !a.two_d) {
@@ -611,7 +644,7 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
   fa2.whitening = a.whitening;
   dim3 grid((g.Kp + 255) / 256, M);
   final_kernel<<<grid, 256, 0, st>>>(g, fa2, L.Xre, L.Xim, L.noise, L.Mg, L.alpha, L.stable,
-                                     L.band_p, L.wt, L.mask, L.Yre, L.Yim);
+                                     L.band_p, a.wt, a.mask, L.Yre, L.Yim);
   SB_LAUNCH_CHECK();
   return true;
 }
