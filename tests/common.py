@@ -1,0 +1,57 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+# BASELINE.json north_star tolerance: max abs error <= 1e-4, residual SNR >= 90 dB
+MAX_ABS_TOL = 1e-4
+SNR_TOL_DB = 90.0
+
+P2D = dict(learn_noise=0, reduction_amount=20.0, smoothing_factor=1.0, whitening_factor=50.0,
+           nlm_masking_protection=0.5, suppression_strength=50.0, aggressiveness=0.0,
+           tonal_reduction=6.0)
+P1D = dict(learn_noise=0, reduction_amount=20.0, smoothing_factor=30.0, whitening_factor=50.0,
+           masking_depth=0.5, suppression_strength=50.0, aggressiveness=1.0, tonal_reduction=0.0)
+
+# must match tests/golden/make_golden.py
+GOLDEN_CASES = {
+    "g2d_48k_manual": (True, 48000, 50.0, 24000, P2D, 4096),
+    "g1d_44k_demo": (False, 44100, 50.0, 8 * 512, P1D, 512),
+    "g2d_44k_spp": (True, 44100, 50.0, 0, dict(P2D, adaptive_noise=1, noise_estimation_method=0), 3000),
+    "g1d_48k_martin": (False, 48000, 20.0, 0, dict(P1D, adaptive_noise=1, noise_estimation_method=2), 1000),
+}
+
+
+def load_golden(name):
+    return np.load(GOLDEN / f"{name}.npz")
+
+
+def parity(out, ref):
+    out = np.asarray(out, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    d = out - ref
+    den = float(np.sum(d * d))
+    snr = 10.0 * np.log10(float(np.sum(ref * ref)) / den) if den > 0 else float("inf")
+    return float(np.max(np.abs(d))) if d.size else 0.0, snr
+
+
+def assert_parity(out, ref, what="", max_abs=MAX_ABS_TOL, snr_db=SNR_TOL_DB):
+    assert np.all(np.isfinite(out)), f"{what}: non-finite output"
+    err, snr = parity(out, ref)
+    assert err <= max_abs and snr >= snr_db, f"{what}: max_abs={err:.3e} snr={snr:.1f} dB"
+    return err, snr
+
+
+def run_flow(d, x, learn, params, chunk):
+    """learn `learn` samples, then denoise the rest, `chunk` samples per process() call."""
+    ys = []
+    if learn:
+        d.load_parameters(learn_noise=1)
+        ys.append(d.process(x[:learn], chunk))
+    d.load_parameters(**params)
+    ys.append(d.process(x[learn:], chunk))
+    return np.concatenate(ys)

@@ -1,0 +1,95 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol
+declared in include/*.h, the parameter struct has the reference's layout, the
+headers are valid C, and without a GPU the product fails loudly (no CPU fallback)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+INCLUDE = ROOT / "include"
+
+
+def declared_functions(header: Path):
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(specbleach_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from libspecbleach_b200 import api
+    L = api.lib()
+    names = []
+    for h in ("specbleach_denoiser.h", "specbleach_2d_denoiser.h", "specbleach_b200.h"):
+        names += declared_functions(INCLUDE / h)
+    assert len(names) >= 22 + 10
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(api.PUBLIC_SYMBOLS) <= set(names) and set(api.EXTENSION_SYMBOLS) <= set(names)
+
+
+def test_public_api_is_the_references_22_symbols():
+    a = declared_functions(INCLUDE / "specbleach_denoiser.h")
+    b = declared_functions(INCLUDE / "specbleach_2d_denoiser.h")
+    assert len(a) == 11 and len(b) == 11
+    assert [n.replace("specbleach_2d_", "specbleach_") for n in b] == a
+
+
+def test_parameter_struct_layout():
+    from libspecbleach_b200.api import DenoiserParameters
+    assert C.sizeof(DenoiserParameters) == 44          # 11 fields, C layout
+    offs = [getattr(DenoiserParameters, f).offset for f, _ in DenoiserParameters._fields_]
+    assert offs == [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40]
+
+
+def test_headers_compile_as_c_and_struct_is_44_bytes(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text(
+        '#include "specbleach_denoiser.h"\n#include "specbleach_2d_denoiser.h"\n'
+        '#include "specbleach_b200.h"\n'
+        "_Static_assert(sizeof(SpectralBleachDenoiserParameters) == 44, \"1D params\");\n"
+        "_Static_assert(sizeof(SpectralBleach2DDenoiserParameters) == 44, \"2D params\");\n"
+        "int main(void) { return specbleach_get_latency(0) + specbleach_2d_get_latency(0); }\n")
+    r = subprocess.run(["gcc", "-std=c17", "-Wall", "-Werror", "-fsyntax-only", f"-I{INCLUDE}", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_null_handle_behaviour_needs_no_gpu():
+    """NULL / bad-argument paths of the reference API (test_specbleach_2d_denoiser.c:34-77)."""
+    from libspecbleach_b200 import api
+    L = api.lib()
+    for pre in ("specbleach_", "specbleach_2d_"):
+        g = lambda n: getattr(L, pre + n)
+        assert g("get_latency")(None) == 0
+        assert g("get_noise_profile_size")(None) == 0
+        assert not g("process")(None, 16, None, None)
+        assert not g("load_parameters")(None, api.make_params())
+        assert not g("reset_noise_profile")(None)
+        assert not g("noise_profile_available_for_mode")(None, 1)
+        assert g("get_noise_profile_block_count_for_mode")(None, 1) == 0
+        assert not g("get_noise_profile_for_mode")(None, 1)
+        g("free")(None)
+    assert not L.specbleach_initialize(0, 50.0)
+    assert not L.specbleach_initialize(3999, 50.0)        # specbleach_denoiser.c:41
+    assert not L.specbleach_initialize(192001, 50.0)
+    assert not L.specbleach_initialize(48000, 0.0)
+    assert not L.specbleach_2d_initialize(0, 50.0)
+    assert not L.specbleach_2d_initialize(48000, -1.0)
+
+
+def test_fails_loudly_without_gpu():
+    import libspecbleach_b200 as sb
+    if sb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sb.Denoiser2D(48000, 50.0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under libspecbleach_b200/ may use it."""
+    pkg = ROOT / "libspecbleach_b200"
+    pat = re.compile(r"(from\s+oracle|import\s+oracle|oracle/|specbleach_np|ref_binding|libspecbleach_ref)")
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")):
+        assert not pat.search(f.read_text()), f
