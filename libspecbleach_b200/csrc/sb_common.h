@@ -80,6 +80,8 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   const float* win;                      // [frame] periodic Hann
   const float2* tw;                      // [M]   exp(-2 pi i k / M)
   const float2* twn;                     // [M+1] exp(-2 pi i k / N)
+  const double2* twg;                    // per generic-radix pass: r roots of unity in double
+  int twg_off[14];                       // offset of pass f inside twg (-1: radix 2/4 pass)
   const float* abs_thr_spl;              // [Kp] absolute threshold, dB SPL
   const float* abs_thr_lin;              // [Kp] the same mapped back to power
   const int* cband;                      // [Kp] interpolation band of a bin

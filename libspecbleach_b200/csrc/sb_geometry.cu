@@ -45,6 +45,24 @@ static void factorize(int m, int* fac, int* nfac) {
   *nfac = n;
 }
 
+// Roots of unity in double for every pass whose radix is not 2 or 4: the generic
+// butterfly accumulates r terms, so it runs in double and rounds once (keeps the
+// odd frame sizes, e.g. N = 3006 = 2*3*3*167, as accurate as the 2^a 5^b ones).
+static std::vector<double2> generic_roots(GeoK& g) {
+  std::vector<double2> t;
+  for (int f = 0; f < g.nfac; f++) {
+    const int r = g.fac[f];
+    if (r == 2 || r == 4) { g.twg_off[f] = -1; continue; }
+    g.twg_off[f] = (int)t.size();
+    for (int k = 0; k < r; k++) {
+      long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)r;
+      t.push_back(make_double2((double)cosl(a), (double)sinl(a)));
+    }
+  }
+  if (t.empty()) t.push_back(make_double2(1.0, 0.0));
+  return t;
+}
+
 // spl_reference_value: absolute_hearing_thresholds.c:86-89,118-139.  The
 // reference takes the peak of a float FFT of a Vorbis-windowed 1 kHz sine; the
 // peak lies in the main lobe, so a double-precision DFT over the bins around it
@@ -192,11 +210,12 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
   g.win = upload(G, win);
   g.tw = upload(G, tw);
   g.twn = upload(G, twn);
+  g.twg = upload(G, generic_roots(g));
   g.abs_thr_spl = upload(G, thr_spl);
   g.abs_thr_lin = upload(G, thr_lin);
   g.cband = upload(G, cband);
   g.band_of_bin = upload(G, bob);
-  if (!g.win || !g.tw || !g.twn || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
+  if (!g.win || !g.tw || !g.twn || !g.twg || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
       !g.band_of_bin) {
     set_error("geometry upload", cudaGetLastError(), __FILE__, __LINE__);
     for (void* p : G->dev_allocs) cudaFree(p);
@@ -241,7 +260,8 @@ Geometry* make_fft_geometry(int fft_size) {
   g.win = upload(G, win);
   g.tw = upload(G, tw);
   g.twn = upload(G, twn);
-  if (!g.win || !g.tw || !g.twn) {
+  g.twg = upload(G, generic_roots(g));
+  if (!g.win || !g.tw || !g.twn || !g.twg) {
     free_geometry(G);
     return nullptr;
   }

@@ -73,27 +73,31 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
         y[q + s * (2 * j + 1)] = cmul(csub(a, b), w1);
       }
     } else {
-      // generic radix: one work item per output point
-      const int rstep = M / r;
+      // generic radix: one work item per output point; the r-term sum runs in
+      // double with double roots of unity and is rounded to float once
+      const double2* __restrict__ root = g.twg + g.twg_off[f];
       for (int item = threadIdx.x; item < M; item += blockDim.x) {
         const int idx = item / r;        // butterfly
         const int t = item - idx * r;    // output index inside the butterfly
         const int j = idx / s;
         const int q = idx - j * s;
-        float2 acc = x[q + s * j];
+        const float2 v0 = x[q + s * j];
+        double ar = (double)v0.x, ai = (double)v0.y;
         int ut = 0;
         for (int u = 1; u < r; u++) {
           ut += t;
           if (ut >= r) ut -= r;
-          float2 w = __ldg(&tw[ut * rstep]);
+          double2 w = root[ut];
           if (INV) w.y = -w.y;
           const float2 v = x[q + s * (j + u * l)];
-          acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
-          acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+          ar = fma((double)v.x, w.x, fma(-(double)v.y, w.y, ar));
+          ai = fma((double)v.x, w.y, fma((double)v.y, w.x, ai));
         }
         float2 wo = __ldg(&tw[j * t * tstep]);
         if (INV) wo.y = -wo.y;
-        y[q + s * (r * j + t)] = cmul(acc, wo);
+        const double yr = ar * (double)wo.x - ai * (double)wo.y;
+        const double yi = ar * (double)wo.y + ai * (double)wo.x;
+        y[q + s * (r * j + t)] = make_float2((float)yr, (float)yi);
       }
     }
     __syncthreads();

@@ -48,7 +48,8 @@ def test_nlm_kernel_vs_reference_module(gpu, ref, F, K, h):
     from libspecbleach_b200 import api
     rng = np.random.default_rng(K)
     s = rng.exponential(1.0, size=(F, K)).astype(np.float32)
-    s[:, K // 3:K // 3 + 40] = 20.0 + 0.05 * rng.standard_normal((F, min(40, K - K // 3))).astype(np.float32)[:, :s[:, K // 3:K // 3 + 40].shape[1]]
+    w = s[:, K // 3:K // 3 + 40].shape[1]
+    s[:, K // 3:K // 3 + 40] = 20.0 + 0.05 * rng.standard_normal((F, w)).astype(np.float32)
     s[:, K // 2:K // 2 + 100] *= 0.01
     s[:, 2 * K // 3:2 * K // 3 + 24] = 0.0
     s[F // 2:, :16] = 0.3
@@ -243,11 +244,7 @@ def test_full_size_properties_config2(gpu, ref):
     assert_parity(short, want, "config2 prefix")
     y2 = run_flow(gpu.Denoiser2D(sr, 50.0), x, sr, P2D, 1 << 20)
     assert np.array_equal(y, y2)                                    # determinism + chunking
-    lat = 2400 + 4 * 600                                            # actual delay: frame + 4*hop
-    noise_in = float(np.mean(x[sr // 2:sr - lat] ** 2))
-    noise_out = float(np.mean(y[sr + 24000 + lat: sr + 24000 + lat + 1] ** 2))  # placeholder sample
     assert float(np.mean(y[2 * sr:] ** 2)) < 0.96 * float(np.mean(x[2 * sr:] ** 2))  # test_audio_regression.c:237
-    assert noise_in > 0 and noise_out >= 0
 
 
 def test_smoke_entry_point(gpu):
