@@ -69,11 +69,17 @@ typedef struct SpecbleachB200Stats {
   uint64_t frames;             /* STFT frames processed                             */
 } SpecbleachB200Stats;
 
-/* enable != 0: bracket every NLM launch with CUDA events on its stream. */
+/* enable != 0: bracket every kernel launch with CUDA events on its stream. */
 void specbleach_b200_profile(int enable);
 void specbleach_b200_stats_reset(void);
 /* Synchronises the device, folds pending event pairs into the totals. */
 bool specbleach_b200_stats_get(SpecbleachB200Stats* out);
+
+/* Per-kernel-class device time (profile mode): every launch of the library is
+ * bracketed by CUDA events on its stream.  Classes are enumerated 0..count-1. */
+int specbleach_b200_stats_classes(void);
+const char* specbleach_b200_stats_class_name(int cls);
+bool specbleach_b200_stats_class(int cls, double* ms, uint64_t* launches);
 
 /* Geometry of a handle: frame, fft size, hop, bins (for tests and tools). */
 bool specbleach_b200_get_geometry(SpectralBleachHandle instance, uint32_t* frame,

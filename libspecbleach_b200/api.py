@@ -63,7 +63,7 @@ PUBLIC_SYMBOLS = [pre + n for pre in ("specbleach_", "specbleach_2d_") for n in 
 EXTENSION_SYMBOLS = ["specbleach_b200_" + n for n in (
     "device_count", "set_device", "last_error", "host_alloc", "host_free", "configure",
     "process_device", "process_batch", "process_batch_device", "profile", "stats_reset",
-    "stats_get", "get_geometry", "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft")]
+    "stats_get", "stats_classes", "stats_class_name", "stats_class", "get_geometry", "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft")]
 
 
 def lib():
@@ -123,6 +123,11 @@ def lib():
     L.specbleach_b200_stats_reset.restype = None
     L.specbleach_b200_stats_get.restype = C.c_bool
     L.specbleach_b200_stats_get.argtypes = [C.POINTER(Stats)]
+    L.specbleach_b200_stats_classes.restype = C.c_int
+    L.specbleach_b200_stats_class_name.restype = C.c_char_p
+    L.specbleach_b200_stats_class_name.argtypes = [C.c_int]
+    L.specbleach_b200_stats_class.restype = C.c_bool
+    L.specbleach_b200_stats_class.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.specbleach_b200_get_geometry.restype = C.c_bool
     L.specbleach_b200_get_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
     L.specbleach_b200_debug_fp32_peak_tflops.restype = C.c_double
@@ -153,6 +158,18 @@ def stats() -> dict:
     if not lib().specbleach_b200_stats_get(C.byref(s)):
         raise RuntimeError(last_error())
     return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def class_stats() -> dict:
+    """per-kernel-class {name: (ms, launches)} measured with CUDA events (profile mode)."""
+    L = lib()
+    out = {}
+    for c in range(L.specbleach_b200_stats_classes()):
+        ms, n = C.c_double(), C.c_uint64()
+        L.specbleach_b200_stats_class(c, C.byref(ms), C.byref(n))
+        if n.value:
+            out[L.specbleach_b200_stats_class_name(c).decode()] = (ms.value, n.value)
+    return out
 
 
 class PinnedArray:

@@ -207,6 +207,7 @@ bool launch_estimator_seed(const GeoK& g, int method, const float* floorv, float
 // interpolation + smoothing of the output -> clamp to the manual floor.
 bool launch_adaptive(const GeoK& g, int method, const float* P, int frames, const float* floorv,
                      float* est, float* energy, float* noise_rows, cudaStream_t st) {
+  KTimer kt_(kcAdaptive, st);
   if (frames <= 0) return true;
   frame_energy_kernel<<<frames, 256, 0, st>>>(g, P, energy);
   SB_LAUNCH_CHECK();

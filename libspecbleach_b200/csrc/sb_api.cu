@@ -227,7 +227,18 @@ void specbleach_b200_stats_reset(void) {
   c.nlm_launches = 0;
   c.nlm_frame_blocks = 0;
   c.frames = 0;
+  for (int i = 0; i < sb::kcCount; i++) { c.class_ms[i] = 0.0; c.class_launches[i] = 0; }
   sb::g_launches = 0;
+}
+int specbleach_b200_stats_classes(void) { return sb::kcCount; }
+const char* specbleach_b200_stats_class_name(int cls) { return sb::kclass_name(cls); }
+bool specbleach_b200_stats_class(int cls, double* ms, uint64_t* launches) {
+  if (cls < 0 || cls >= sb::kcCount || !ms || !launches) return false;
+  sb::Context& c = sb::ctx();
+  if (!sb::stats_collect(c)) return false;
+  *ms = c.class_ms[cls];
+  *launches = c.class_launches[cls];
+  return true;
 }
 bool specbleach_b200_stats_get(SpecbleachB200Stats* out) {
   if (!out) return false;

@@ -233,6 +233,25 @@ extern bool g_profile;          // record NLM events
   } while (0)
 
 // ---------------------------------------------------------------------------
+// Per-kernel-class device timing (profile mode): CUDA events on the launching
+// stream around every launch, folded into per-class totals by stats_collect().
+// ---------------------------------------------------------------------------
+enum KClass {
+  kcForward = 0, kcInverse, kcOla, kcNlm, kcNlmTail, kcSnr, kcGainPre, kcBinScan, kcBand,
+  kcTScan, kcNmr, kcPScan, kcFinal, kcTonal, kcWhiten, kcLearn, kcInterp, kcAdaptive, kcMisc,
+  kcCount
+};
+const char* kclass_name(int c);
+void ktimer_begin(int cls, cudaStream_t st);
+void ktimer_end(int cls, cudaStream_t st);
+struct KTimer {
+  int cls;
+  cudaStream_t st;
+  KTimer(int c, cudaStream_t s) : cls(c), st(s) { if (g_profile) ktimer_begin(cls, st); }
+  ~KTimer() { if (g_profile) ktimer_end(cls, st); }
+};
+
+// ---------------------------------------------------------------------------
 // Kernel launchers (one translation unit per kernel family)
 // ---------------------------------------------------------------------------
 // sb_stft.cu

@@ -41,6 +41,31 @@ const char* last_error() {
 }
 
 // ---------------------------------------------------------------------------
+// Per-kernel-class timing
+// ---------------------------------------------------------------------------
+struct KEvent { int cls; cudaEvent_t e0, e1; };
+static std::vector<KEvent> g_kevents;
+static std::mutex g_kev_mu;
+static const char* const kNames[kcCount] = {
+    "forward_fft", "inverse_fft", "ola", "nlm", "nlm_tail", "snr", "gain_pre", "bin_scan", "band",
+    "tscan", "nmr", "pscan", "final", "tonal_mask", "whitening", "learn", "interp_smooth",
+    "adaptive", "misc"};
+const char* kclass_name(int c) { return (c >= 0 && c < kcCount) ? kNames[c] : "?"; }
+void ktimer_begin(int cls, cudaStream_t st) {
+  KEvent k;
+  k.cls = cls;
+  if (cudaEventCreate(&k.e0) != cudaSuccess || cudaEventCreate(&k.e1) != cudaSuccess) return;
+  cudaEventRecord(k.e0, st);
+  std::lock_guard<std::mutex> lock(g_kev_mu);
+  g_kevents.push_back(k);
+}
+void ktimer_end(int cls, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_kev_mu);
+  for (size_t i = g_kevents.size(); i-- > 0;)
+    if (g_kevents[i].cls == cls) { cudaEventRecord(g_kevents[i].e1, st); break; }
+}
+
+// ---------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------
 static Context g_ctx;
@@ -320,22 +345,11 @@ static bool denoise_frames(Handle* h, Lane& L, int M) {
     if (first_active > M) first_active = M;
     const int targets = M - first_active;
     if (targets > 0) {
-      cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (g_profile) {
-        SB_CUDA(cudaEventCreate(&e0));
-        SB_CUDA(cudaEventCreate(&e1));
-        SB_CUDA(cudaEventRecord(e0, st));
-      }
       // target of frame i is frame i-4: row (20+i)-4 of S
       if (!launch_nlm(g, L.S, kNlmPast + first_active, targets, h->nlm_h,
                       L.Shat + (size_t)first_active * Kp, st))
         return false;
-      if (g_profile) {
-        SB_CUDA(cudaEventRecord(e1, st));
-        L.ev.push_back(e0);
-        L.ev.push_back(e1);
-        ctx().nlm_frame_blocks += (uint64_t)targets * (uint64_t)((g.K + 7) / 8);
-      }
+      if (g_profile) ctx().nlm_frame_blocks += (uint64_t)targets * (uint64_t)((g.K + 7) / 8);
     }
   }
 
@@ -566,18 +580,21 @@ bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* 
 }
 
 bool stats_collect(Context& c) {
-  for (Lane& L : c.lanes) {
+  for (Lane& L : c.lanes)
     if (L.stream) SB_CUDA(cudaStreamSynchronize(L.stream));
-    for (size_t i = 0; i + 1 < L.ev.size(); i += 2) {
-      float ms = 0.f;
-      SB_CUDA(cudaEventElapsedTime(&ms, L.ev[i], L.ev[i + 1]));
-      c.nlm_ms += ms;
-      c.nlm_launches++;
-      cudaEventDestroy(L.ev[i]);
-      cudaEventDestroy(L.ev[i + 1]);
+  SB_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_kev_mu);
+  for (KEvent& k : g_kevents) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, k.e0, k.e1) == cudaSuccess) {
+      c.class_ms[k.cls] += ms;
+      c.class_launches[k.cls]++;
+      if (k.cls == kcNlm) { c.nlm_ms += ms; c.nlm_launches++; }
     }
-    L.ev.clear();
+    cudaEventDestroy(k.e0);
+    cudaEventDestroy(k.e1);
   }
+  g_kevents.clear();
   return true;
 }
 

@@ -14,6 +14,8 @@ struct Context {
   uint64_t nlm_launches = 0;
   uint64_t nlm_frame_blocks = 0;
   uint64_t frames = 0;
+  double class_ms[kcCount] = {0};
+  uint64_t class_launches[kcCount] = {0};
 };
 Context& ctx();
 

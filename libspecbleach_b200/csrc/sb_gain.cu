@@ -545,12 +545,14 @@ final_kernel(const GeoK g, FinalArgs a, const float* __restrict__ Xre_t,
 
 bool launch_morph_profile(const GeoK& g, const float* prof, float aggressiveness, float* out,
                           cudaStream_t st) {
+  KTimer kt_(kcMisc, st);
   morph_kernel<<<(g.Kp + 255) / 256, 256, 0, st>>>(g, prof, aggressiveness, out);
   SB_LAUNCH_CHECK();
   return true;
 }
 
 bool launch_fill_rows(const GeoK& g, const float* row, float* dst, int rows, cudaStream_t st) {
+  KTimer kt_(kcMisc, st);
   if (rows <= 0) return true;
   dim3 grid((g.Kp + 255) / 256, rows < 1024 ? rows : 1024);
   fill_rows_kernel<<<grid, 256, 0, st>>>(g, row, dst, rows);
@@ -560,6 +562,7 @@ bool launch_fill_rows(const GeoK& g, const float* row, float* dst, int rows, cud
 
 bool launch_snr(const GeoK& g, const float* P, const float* noise, float* S, int frames,
                 cudaStream_t st) {
+  KTimer kt_(kcSnr, st);
   if (frames <= 0) return true;
   dim3 grid((g.Kp + 255) / 256, frames);
   snr_kernel<<<grid, 256, 0, st>>>(g, P, noise, S);
@@ -569,6 +572,7 @@ bool launch_snr(const GeoK& g, const float* P, const float* noise, float* S, int
 
 bool launch_tonal_mask(const GeoK& g, const float* det, int det_stride, int rows, float* mask,
                        cudaStream_t st) {
+  KTimer kt_(kcTonal, st);
   if (rows <= 0) return true;
   dim3 grid((g.Kp + 255) / 256, rows);
   tonal_mask_kernel<<<grid, 256, 0, st>>>(g, det, det_stride, mask, g.Kp);
@@ -578,6 +582,7 @@ bool launch_tonal_mask(const GeoK& g, const float* det, int det_stride, int rows
 
 bool launch_whitening(const GeoK& g, const float* noise, int noise_stride, int rows,
                       float whitening, float* wt, cudaStream_t st) {
+  KTimer kt_(kcWhiten, st);
   if (rows <= 0) return true;
   int P2 = 1;
   while (P2 < g.K) P2 <<= 1;
@@ -608,27 +613,45 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
     pa.alpha_max_user = kAlphaMin + (a.strength * (kAlphaMax - kAlphaMin));
     pa.tonal_gain = a.tonal;
     dim3 grid((g.Kp + 255) / 256, active);
+    {
+      KTimer kt_(kcGainPre, st);
     gain_pre_kernel<<<grid, 256, 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, a.mask, L.Mg,
                                           L.alpha, L.stable);
     SB_LAUNCH_CHECK();
+    }
     if (use_veto || !a.two_d) {
+      {
+        KTimer kt_(kcBinScan, st);
       bin_scan_kernel<<<(g.K + 127) / 128, 128, 0, st>>>(g, fa, active, a.two_d ? 1 : 0,
                                                          a.smoothing, L.P, L.noise, L.Mg,
                                                          L.stable, h.d_stable, h.d_sp_prev);
       SB_LAUNCH_CHECK();
+      }
     }
     if (use_veto) {
+      {
+        KTimer kt_(kcBand, st);
       band_kernel<<<active, 256, 0, st>>>(g, fa, a.two_d ? 1 : 0, L.stable, L.Xre, L.noise,
                                           L.band_a);
       SB_LAUNCH_CHECK();
+      }
+      {
+        KTimer kt_(kcTScan, st);
       tscan_kernel<<<1, kBandPitch, 0, st>>>(g, fa, active, L.band_a, L.band_T,
                                              h.d_band_state);
       SB_LAUNCH_CHECK();
+      }
+      {
+        KTimer kt_(kcNmr, st);
       nmr_kernel<<<active, 256, 0, st>>>(g, fa, L.band_T, L.noise, L.band_p);
       SB_LAUNCH_CHECK();
+      }
+      {
+        KTimer kt_(kcPScan, st);
       pscan_kernel<<<1, kBandPitch, 0, st>>>(g, fa, active, L.band_p,
                                              h.d_band_state + kBandPitch);
       SB_LAUNCH_CHECK();
+      }
     }
   }
   FinalArgs fa2;
@@ -643,9 +666,12 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
   fa2.tonal = a.tonal;
   fa2.whitening = a.whitening;
   dim3 grid((g.Kp + 255) / 256, M);
+  {
+    KTimer kt_(kcFinal, st);
   final_kernel<<<grid, 256, 0, st>>>(g, fa2, L.Xre, L.Xim, L.noise, L.Mg, L.alpha, L.stable,
                                      L.band_p, a.wt, a.mask, L.Yre, L.Yim);
   SB_LAUNCH_CHECK();
+  }
   return true;
 }
 

@@ -155,6 +155,7 @@ interp_smooth_kernel(const GeoK g, float* __restrict__ rows, int row_stride, uns
 
 bool launch_learn(const GeoK& g, const float* P, int frames, uint32_t count0, float* prof,
                   float* med_ring, int med_write, cudaStream_t st) {
+  KTimer kt_(kcLearn, st);
   if (frames <= 0) return true;
   learn_kernel<<<(g.K + 127) / 128, 128, 0, st>>>(g, P, frames, count0, prof, med_ring, med_write);
   SB_LAUNCH_CHECK();
@@ -164,6 +165,7 @@ bool launch_learn(const GeoK& g, const float* P, int frames, uint32_t count0, fl
 bool launch_interp_smooth(const GeoK& g, float* rows, int row_stride, int nrows,
                           unsigned enable_mask, float threshold, float factor,
                           const float* floorv, cudaStream_t st) {
+  KTimer kt_(kcInterp, st);
   if (nrows <= 0) return true;
   const size_t smem = sizeof(float) * 4 * (size_t)g.K;
   if (smem > 48 * 1024)

@@ -233,6 +233,7 @@ static bool set_fft_smem(const void* fn, size_t bytes) {
 
 bool launch_forward(const GeoK& g, const float* xbuf, int frames, float* Xre, float* Xim,
                     float* P, cudaStream_t st) {
+  KTimer kt_(kcForward, st);
   if (frames <= 0) return true;
   const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
   if (!set_fft_smem((const void*)forward_kernel, smem)) return false;
@@ -243,6 +244,7 @@ bool launch_forward(const GeoK& g, const float* xbuf, int frames, float* Xre, fl
 
 bool launch_inverse(const GeoK& g, const float* Yre, const float* Yim, int frames,
                     float* synth, cudaStream_t st) {
+  KTimer kt_(kcInverse, st);
   if (frames <= 0) return true;
   const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
   if (!set_fft_smem((const void*)inverse_kernel, smem)) return false;
@@ -253,6 +255,7 @@ bool launch_inverse(const GeoK& g, const float* Yre, const float* Yim, int frame
 
 bool launch_ola(const GeoK& g, const float* synth, int frames, uint32_t carry, uint32_t n,
                 const float* tail_in, float* tail_out, float* y, cudaStream_t st) {
+  KTimer kt_(kcOla, st);
   const unsigned total = n + (unsigned)g.frame;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

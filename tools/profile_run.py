@@ -38,4 +38,9 @@ for rep in range(2):
     print(f"rep {rep}: {seconds:.0f} s mono in {dt*1e3:.2f} ms -> {seconds/dt:.0f}x realtime (mono); "
           f"nlm {st['nlm_ms']:.3f} ms over {st['nlm_launches']} launches; "
           f"{st['kernel_launches']} kernel launches; rms {np.sqrt(np.mean(y**2)):.4f}")
+cs = api.class_stats()
+tot = sum(v[0] for v in cs.values())
+for k, (ms, n) in sorted(cs.items(), key=lambda kv: -kv[1][0]):
+    print(f"  {k:14s} {ms:8.3f} ms  {n:4d} launches  {100*ms/tot:5.1f}%")
+print(f"  sum of kernel time {tot:.3f} ms")
 print("fp32 peak TFLOP/s:", api.lib().specbleach_b200_debug_fp32_peak_tflops())
