@@ -9,6 +9,7 @@
 //        spp_mmse_noise_estimator.c:28-62,98-194
 //   martin_noise_estimator_run / _set_state / _apply_floor
 //        martin_noise_estimator.c:82-209
+//   brandt_noise_estimator_*: sb_brandt.cu
 //   adaptive_estimator_run tail (gap interpolation + smoothing of the OUTPUT)
 //        adaptive_noise_estimator.c:156-187   (done by interp_smooth_kernel)
 //   denoiser_profile_core_update adaptive branch  denoiser_profile_core.c:55-88
@@ -192,12 +193,14 @@ __global__ void martin_scan_kernel(const GeoK g, const float* __restrict__ P,
 }  // namespace
 
 size_t estimator_floats(const GeoK& g, int method) {
+  if (method == kBrandt) return brandt_estimator_floats(g);
   const size_t per_bin = (method == kSpp) ? 2 : (2 + kMartinSubwinCount);
   return kEstHeader + per_bin * (size_t)g.Kp;
 }
 
 bool launch_estimator_seed(const GeoK& g, int method, const float* floorv, float* est,
                            cudaStream_t st) {
+  if (method == kBrandt) return launch_brandt_seed(g, floorv, est, st);
   seed_kernel<<<(g.K + 255) / 256, 256, 0, st>>>(g, method, floorv, est);
   SB_LAUNCH_CHECK();
   return true;
@@ -206,18 +209,22 @@ bool launch_estimator_seed(const GeoK& g, int method, const float* floorv, float
 // Produces the per-frame noise rows of a call: estimator scan -> gap
 // interpolation + smoothing of the output -> clamp to the manual floor.
 bool launch_adaptive(const GeoK& g, int method, const float* P, int frames, const float* floorv,
-                     float* est, float* energy, float* noise_rows, cudaStream_t st) {
+                     float* est, float* energy, int* idx_scratch, bool fresh_seed,
+                     float* noise_rows, cudaStream_t st) {
   KTimer kt_(kcAdaptive, st);
   if (frames <= 0) return true;
   frame_energy_kernel<<<frames, 256, 0, st>>>(g, P, energy);
   SB_LAUNCH_CHECK();
-  if (method == kSpp) {
+  if (method == kBrandt) {
+    if (!launch_brandt(g, P, frames, floorv, est, energy, idx_scratch, fresh_seed, noise_rows, st))
+      return false;
+  } else if (method == kSpp) {
     spp_scan_kernel<<<(g.K + 63) / 64, 64, 0, st>>>(g, P, energy, frames, floorv, est, noise_rows);
   } else {
     martin_scan_kernel<<<(g.K + 63) / 64, 64, 0, st>>>(g, P, energy, frames, floorv, est,
                                                        noise_rows);
   }
-  SB_LAUNCH_CHECK();
+  if (method != kBrandt) SB_LAUNCH_CHECK();
   return launch_interp_smooth(g, noise_rows, g.Kp, frames, 0xffffffffu, kInterpThreshold,
                               kNoiseSmoothing, floorv, st);
 }

@@ -300,7 +300,20 @@ bool launch_interp_smooth(const GeoK& g, float* rows, int row_stride, int nrows,
 size_t estimator_floats(const GeoK& g, int method);
 bool launch_estimator_seed(const GeoK& g, int method, const float* floorv, float* est,
                            cudaStream_t st);
+// idx_scratch: >= frames + 1 ints of lane scratch (Brandt: compacted non-silent frames);
+// fresh_seed: launch_estimator_seed ran for this very call.
 bool launch_adaptive(const GeoK& g, int method, const float* P, int frames, const float* floorv,
-                     float* est, float* energy, float* noise_rows, cudaStream_t st);
+                     float* est, float* energy, int* idx_scratch, bool fresh_seed,
+                     float* noise_rows, cudaStream_t st);
+
+// sb_brandt.cu
+void set_error_msg(const char* msg);   // sb_engine.cu
+size_t brandt_estimator_floats(const GeoK& g);
+int brandt_history(const GeoK& g);
+bool brandt_supported(const GeoK& g);
+bool launch_brandt_seed(const GeoK& g, const float* floorv, float* est, cudaStream_t st);
+bool launch_brandt(const GeoK& g, const float* P, int frames, const float* floorv, float* est,
+                   const float* energy, int* idx, bool fresh_seed, float* noise_rows,
+                   cudaStream_t st);
 
 }  // namespace sb

@@ -198,8 +198,8 @@ bool handle_load_parameters(Handle* h, const Params& p) {
   if (p.adaptive) {
     int requested = p.method;
     if (requested != kSpp && requested != kBrandt && requested != kMartin) requested = kMartin;
-    if (requested == kBrandt) {
-      set_error_msg("specbleach-b200: Brandt estimator is not implemented on the GPU path yet");
+    if (requested == kBrandt && !brandt_supported(h->geo->k)) {
+      set_error_msg("specbleach-b200: Brandt history too long for this frame size");
       return false;
     }
     if (h->est_method != requested) {
@@ -321,13 +321,15 @@ static bool denoise_frames(Handle* h, Lane& L, int M) {
   if (adaptive) {
     const bool state_changed = h->last_adaptive_state == 0;
     const bool mode_changed = fabsf(h->aggressiveness_state - p.aggressiveness) > 0.01f;
-    if (state_changed || mode_changed) {
+    const bool fresh_seed = state_changed || mode_changed;
+    if (fresh_seed) {
       if (!launch_morph_profile(g, h->d_prof, p.aggressiveness, h->d_floor, st)) return false;
       if (!launch_estimator_seed(g, h->est_method, h->d_floor, h->d_est, st)) return false;
       h->last_adaptive_state = 1;
     }
-    if (!launch_adaptive(g, h->est_method, L.P, M, h->d_floor, h->d_est, L.frame_flag, noise_new,
-                         st))
+    // L.band_a ([F][32] floats) is free until the gain chain: scratch for the frame index list
+    if (!launch_adaptive(g, h->est_method, L.P, M, h->d_floor, h->d_est, L.frame_flag,
+                         reinterpret_cast<int*>(L.band_a), fresh_seed, noise_new, st))
       return false;
     h->aggressiveness_state = p.aggressiveness;
   } else {

@@ -2,8 +2,8 @@
 
 This file is the *oracle* of specbleach-b200: an independent, readable, float32
 restatement of what ``/root/reference`` computes for ``specbleach_process`` and
-``specbleach_2d_process`` (learn mode, manual profile, SPP-MMSE and Martin
-adaptive estimators).  It is pinned against the reference itself:
+``specbleach_2d_process`` (learn mode, manual profile, SPP-MMSE, Martin
+and Brandt adaptive estimators).  It is pinned against the reference itself:
 ``tests/test_oracle.py`` checks it against ``oracle/_ref`` (the unmodified reference
 sources compiled by ``oracle/Makefile``) and against the committed golden vectors in
 ``tests/golden/`` that were generated from that build.  Only ``tests/``,
@@ -13,7 +13,6 @@ never does.
 Every function cites the reference lines it restates (paths relative to the
 reference tree).  The FFT (FFTW3f in the reference, un-vendored third party) is
 evaluated with numpy's double-precision pocketfft and rounded to float32 once.
-Not restated: the Brandt estimator.
 """
 from __future__ import annotations
 
@@ -301,6 +300,8 @@ class OracleDenoiser:
             self.est = {"method": p.method, "first": True, "psd": np.zeros(K, f32),
                         "sspp": np.zeros(K, f32), "cmin": np.zeros(K, f32),
                         "hist": np.zeros((8, K), f32), "fc": 0, "idx": 0}
+            if p.method == 1:
+                self.est.update(brandt_init(K, self.sr, self.g.N))
             self.last_adaptive_state = 0
         self.prm = p
         if self.two_d and p.smoothing > 0:
@@ -538,6 +539,8 @@ class OracleDenoiser:
     # -- adaptive estimators --
     def _seed(self, fl):
         e = self.est
+        if e["method"] == 1:
+            return brandt_set_state(e, fl)
         v = np.maximum(fl, FLT_MIN)
         if e["method"] == 0:                                             # spp_mmse:169-180
             e["psd"] = v.copy()
@@ -551,6 +554,8 @@ class OracleDenoiser:
 
     def _apply_floor(self, fl):
         e = self.est
+        if e["method"] == 1:
+            return brandt_apply_floor(e, fl)
         e["psd"] = np.maximum(e["psd"], fl)
         if e["method"] != 0:
             e["cmin"] = np.maximum(e["cmin"], fl)
@@ -561,6 +566,8 @@ class OracleDenoiser:
         K = P.size
         energy = f32(np.sum(P, dtype=f32) / f32(K))
         silent = energy < f32(1e-10)
+        if e["method"] == 1:
+            return brandt_run(e, P, energy)
         if e["method"] == 0:                                             # spp_mmse:98-166
             if e["first"]:
                 if silent:
@@ -597,6 +604,118 @@ class OracleDenoiser:
         out = (np.minimum(e["cmin"], e["hist"].min(axis=0)) * f32(1.5)).astype(f32)
         e["fc"] += 1
         return out
+
+
+# ---------------------------------------------------------------------------
+# Brandt trimmed-mean estimator (brandt_noise_estimator.c)
+# ---------------------------------------------------------------------------
+BRANDT_P = (f32(0.1), f32(0.25), f32(0.5), f32(0.75), f32(1.0))
+
+
+def brandt_correction(p) -> np.float32:
+    """calculate_correction_factor, brandt_noise_estimator.c:44-56."""
+    p = f32(p)
+    if p <= 0 or p >= 1:
+        return f32(1.0)
+    den = f32(1.0) + (f32(1.0) - p) / p * f32(np.log(f32(1.0) - p))
+    return f32(1.0) if abs(den) < f32(1e-6) else f32(f32(1.0) / f32(den))
+
+
+def brandt_init(K: int, sr: int, N: int) -> dict:
+    """brandt_noise_estimator_initialize, brandt_noise_estimator.c:65-128: the history
+    length assumes a hop of fft_size/2 (quirk Q6)."""
+    frame_dur = max(f32(f32(N) * f32(1000.0) / f32(sr)) * f32(0.5), f32(0.1))
+    H = max(int(f32(5000.0) / frame_dur), 5)
+    return {"H": H, "bh": np.zeros((K, H), f32), "bidx": 0, "last": np.zeros(K, f32),
+            "bfirst": True, "cf": brandt_correction(0.5),
+            "cfs": [brandt_correction(p) for p in BRANDT_P]}
+
+
+def brandt_set_state(e: dict, profile: np.ndarray) -> None:
+    """brandt_noise_estimator_set_state / _update_seed, :252-282: history = profile /
+    factor(0.5) with a deterministic +-1 % jitter indexed by (t + k) % 11."""
+    K, H = e["bh"].shape
+    val = (profile * (f32(1.0) / e["cf"])).astype(f32)
+    t = np.arange(H)[None, :] + np.arange(K)[:, None]
+    jitter = (f32(1.0) + f32(0.01) * ((t % 11) - 5).astype(f32) / f32(5.0)).astype(f32)
+    e["bh"] = (val[:, None] * jitter).astype(f32)
+    e["last"] = profile.astype(f32).copy()
+    e["bfirst"] = False
+
+
+def brandt_apply_floor(e: dict, fl: np.ndarray) -> None:
+    """brandt_noise_estimator_apply_floor, :284-299."""
+    fv = (fl * (f32(1.0) / e["cf"])).astype(f32)
+    e["bh"] = np.maximum(e["bh"], fv[:, None])
+
+
+def _gcc_vector_sum(s: np.ndarray, q: int) -> np.ndarray:
+    """sum of s[:, :q] in the order gcc -O3 -ffast-math -mavx2 emits for the scalar loop at
+    brandt_noise_estimator.c:218-221 (8-lane partial sums, fold to 4 lanes, one more
+    4-vector, horizontal add, <= 3 scalar leftovers); verified on the oracle build."""
+    K = s.shape[0]
+    n8 = q // 8
+    acc = np.zeros((K, 8), f32)
+    for j in range(n8):
+        acc = acc + s[:, 8 * j:8 * j + 8]
+    a4 = acc[:, :4] + acc[:, 4:]
+    done = 8 * n8
+    if q - done >= 4:
+        a4 = a4 + s[:, done:done + 4]
+        done += 4
+    tot = (a4[:, 1] + a4[:, 3]) + (a4[:, 0] + a4[:, 2])
+    for j in range(done, q):
+        tot = tot + s[:, j]
+    return tot.astype(f32)
+
+
+def brandt_run(e: dict, P: np.ndarray, energy) -> np.ndarray:
+    """brandt_noise_estimator_run, :134-250 (all bins at once)."""
+    K, H = e["bh"].shape
+    thr = f32(1e-10)
+    if e["bfirst"] and energy > thr:
+        brandt_set_state(e, P)                  # same fill as :147-160 (factor(0.5) == cf)
+        e["last"] = P.copy()
+    if energy < thr:
+        return e["last"].copy()
+    e["bh"][:, e["bidx"]] = P
+    e["bidx"] = (e["bidx"] + 1) % H
+    s = np.sort(e["bh"], axis=1)
+    min_ad = np.full(K, f32(2.0))
+    best = e["last"].copy()
+    for ci, p in enumerate(BRANDT_P):
+        q = int(f32(p) * f32(H))
+        if q < 10:
+            continue
+        b = s[:, q - 1]
+        mu_trunc = _gcc_vector_sum(s, q) / f32(q)
+        ok = mu_trunc > thr
+        mu = (mu_trunc * e["cfs"][ci]).astype(f32)
+        ad = np.ones(K, f32)                    # calculate_ad_norm, :113-132
+        live = ok & (mu >= f32(1e-15))
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            mu_inv = (f32(1.0) / mu).astype(f32)
+            denom = (f32(1.0) - np.exp(-(b * mu_inv).astype(f32), dtype=f32)).astype(f32)
+            live &= ~(np.abs(denom) < f32(1e-12))
+            q_inv = f32(1.0) / f32(q)
+            denom_inv = (f32(1.0) / denom).astype(f32)
+            e1 = (f32(1.0) - np.exp(-(s[:, :q] * mu_inv[:, None]).astype(f32), dtype=f32)).astype(f32)
+            f_emp = (np.arange(1, q + 1, dtype=f32) * q_inv).astype(f32)
+            # gcc contracts f_emp - e1*denom_inv into one vfnmadd (single rounding)
+            term = np.abs((f_emp[None, :].astype(np.float64)
+                           - e1.astype(np.float64) * denom_inv[:, None].astype(np.float64))
+                          .astype(f32))
+            tot = np.zeros(K, f32)
+            for i in range(q):                  # sequential scalar accumulation
+                tot = tot + term[:, i]
+            adv = ((tot + tot) * q_inv).astype(f32)
+        ad = np.where(live, adv, ad).astype(f32)
+        upd = ok & (ad < min_ad)
+        best = np.where(upd, mu, best)
+        min_ad = np.where(ok, np.minimum(min_ad, ad), min_ad)
+    accept = ~(f32(1.0) - f32(0.9) < min_ad)    # 1 - min_ad >= 0.9 as gcc folds it
+    e["last"] = np.where(accept, best, e["last"]).astype(f32)
+    return e["last"].copy()
 
 
 def run(x: np.ndarray, sr: int, frame_ms: float, two_d: bool, learn_samples: int, params: dict,

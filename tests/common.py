@@ -23,6 +23,9 @@ GOLDEN_CASES = {
     "g1d_44k_demo": (False, 44100, 50.0, 8 * 512, P1D, 512),
     "g2d_44k_spp": (True, 44100, 50.0, 0, dict(P2D, adaptive_noise=1, noise_estimation_method=0), 3000),
     "g1d_48k_martin": (False, 48000, 20.0, 0, dict(P1D, adaptive_noise=1, noise_estimation_method=2), 1000),
+    "g2d_48k_brandt": (True, 48000, 50.0, 0, dict(P2D, adaptive_noise=1, noise_estimation_method=1), 5000),
+    "g1d_44k_brandt_learned": (False, 44100, 20.0, 8820,
+                               dict(P1D, adaptive_noise=1, noise_estimation_method=1), 2048),
 }
 
 
@@ -55,3 +58,30 @@ def run_flow(d, x, learn, params, chunk):
     d.load_parameters(**params)
     ys.append(d.process(x[learn:], chunk))
     return np.concatenate(ys)
+
+
+def assert_parity_discontinuous(got, make_ref, x, what="", trials=3):
+    """Parity for the Brandt estimator, whose arg-min over five fits and 0.90 confidence
+    gate are discontinuous: when two fits tie to ~1e-7 the reference's own choice flips
+    under a 1-ULP perturbation of its input ("Brandt knife edges"), so no
+    implementation with a different FFT rounding can follow it.  The CUDA output must be
+    within the BASELINE tolerance of the reference on the exact input, or -- only if the
+    reference itself is unstable there -- of the reference on a 1-ULP-perturbed input."""
+    want = make_ref(x)
+    err, snr = parity(got, want)
+    if err <= MAX_ABS_TOL and snr >= SNR_TOL_DB:
+        return "exact-input reference", err, snr
+    rng = np.random.default_rng(1)
+    best = (err, snr)
+    for _ in range(trials):
+        xp = (x * (1.0 + 6e-8 * rng.standard_normal(x.size))).astype(np.float32)
+        alt = make_ref(xp)
+        e_self, s_self = parity(alt, want)
+        e, s_ = parity(got, alt)
+        best = min(best, (e, s_))
+        if e <= MAX_ABS_TOL and s_ >= SNR_TOL_DB:
+            assert e_self > MAX_ABS_TOL or s_self < SNR_TOL_DB, \
+                f"{what}: reference is stable here, yet the CUDA path misses it ({err:.3e}, {snr:.1f} dB)"
+            return "1-ULP-perturbed reference (reference unstable: %.1f dB vs itself)" % s_self, e, s_
+    raise AssertionError(f"{what}: max_abs={err:.3e} snr={snr:.1f} dB vs the reference; "
+                         f"best vs perturbed references {best[0]:.3e} / {best[1]:.1f} dB")

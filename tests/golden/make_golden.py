@@ -33,11 +33,17 @@ CASES = {
                     dict(P2D, adaptive_noise=1, noise_estimation_method=0), 3000, "noise", 44),
     "g1d_48k_martin": (False, 48000, 20.0, 1.0, 0,
                        dict(P1D, adaptive_noise=1, noise_estimation_method=2), 1000, "noise", 45),
+    "g2d_48k_brandt": (True, 48000, 50.0, 1.5, 0,
+                       dict(P2D, adaptive_noise=1, noise_estimation_method=1), 5000, "noise", 46),
+    "g1d_44k_brandt_learned": (False, 44100, 20.0, 1.6, 8820,
+                               dict(P1D, adaptive_noise=1, noise_estimation_method=1), 2048, "speech", 47),
 }
 
 
-def main():
+def main(only=None):
     for name, (two_d, sr, ms, secs, learn, prm, chunk, gen, seed) in CASES.items():
+        if only and name not in only:
+            continue
         x = speech_plus_noise(secs, sr, seed) if gen == "speech" else nonstationary_noise(secs, sr, seed)
         d = rb.RefDenoiser(sr, ms, two_d)
         ys = []
@@ -52,6 +58,8 @@ def main():
         np.savez_compressed(OUT / f"{name}.npz", x=x, y=y, profiles_after_learn=profiles,
                             blocks=blocks, latency=d.latency(), profile_size=d.profile_size())
         print(name, x.shape, float(np.sqrt(np.mean(y ** 2))))
+    if only:
+        return
     # NLM module on its own (nlm_filter.c), incl. a partial last block (203 % 8 = 3)
     rng = np.random.default_rng(7)
     s = rng.exponential(1.0, (27, 203)).astype(np.float32)
@@ -63,4 +71,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

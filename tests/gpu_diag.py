@@ -169,6 +169,36 @@ def check_adaptive():
             emit(check="adaptive", case=name, error=repr(e), tb=traceback.format_exc()[-800:])
 
 
+def check_brandt():
+    x = nonstationary_noise(6.0, 44100, 20260004)
+    for name, two_d, ms, learn in (("2d_brandt", True, 50.0, 0), ("1d_brandt_20ms", False, 20.0, 0),
+                                   ("2d_brandt_learned", True, 50.0, 44100)):
+        try:
+            base = PARAMS_2D if two_d else PARAMS_1D
+            prm = dict(base, adaptive_noise=1, noise_estimation_method=1)
+            t0 = time.perf_counter()
+            yr, yg, _, meta = run_pair(two_d, 44100, ms, x, learn, prm, None, 10000)
+            emit(check="brandt", case=name, secs=time.perf_counter() - t0,
+                 rms_ref=float(np.sqrt(np.mean(yr ** 2))), **cmp(yg, yr))
+        except Exception as e:  # noqa: BLE001
+            emit(check="brandt", case=name, error=repr(e), tb=traceback.format_exc()[-800:])
+    # throughput of the estimator on its own: 60 s mono, 1D (no NLM)
+    sr = 48000
+    xs = nonstationary_noise(60.0, sr, 5)
+    d = sb.Denoiser(sr, 50.0, False)
+    d.load_parameters(**dict(PARAMS_1D, adaptive_noise=1, noise_estimation_method=1))
+    d.process(xs[:sr * 5])
+    api.lib().specbleach_b200_profile(1)
+    api.lib().specbleach_b200_stats_reset()
+    t0 = time.perf_counter()
+    d.process(xs)
+    dt = time.perf_counter() - t0
+    emit(check="brandt_speed", audio_s=60.0, secs=dt, x_realtime=60.0 / dt,
+         classes={k: v[0] for k, v in api.class_stats().items()})
+    api.lib().specbleach_b200_profile(0)
+    d.close()
+
+
 def check_speed():
     sr = 48000
     x = speech_plus_noise(61.0, sr, 3)
@@ -192,7 +222,8 @@ def check_speed():
 if __name__ == "__main__":
     emit(check="env", devices=sb.device_count(), ref=rb.available())
     only = set(sys.argv[1:])
-    for fn in (check_fft, check_nlm, check_learn, check_denoise, check_adaptive, check_speed):
+    for fn in (check_fft, check_nlm, check_learn, check_denoise, check_adaptive, check_brandt,
+               check_speed):
         if not only or fn.__name__ in only:
             section(fn)
     emit(check="done")

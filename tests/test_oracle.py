@@ -25,7 +25,8 @@ class NpDenoiser:
         return np.concatenate([self.d.process(x[i:i + chunk]) for i in range(0, len(x), chunk)])
 
 
-@pytest.mark.parametrize("name", ["g1d_44k_demo", "g1d_48k_martin", "g2d_48k_manual"])
+@pytest.mark.parametrize("name", ["g1d_44k_demo", "g1d_48k_martin", "g2d_48k_manual", "g2d_48k_brandt",
+                                  "g1d_44k_brandt_learned"])
 def test_restatement_matches_golden(name):
     two_d, sr, ms, learn, prm, chunk = GOLDEN_CASES[name]
     g = load_golden(name)
