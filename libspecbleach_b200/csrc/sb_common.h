@@ -266,6 +266,10 @@ bool launch_ola(const GeoK& g, const float* synth, int frames, uint32_t carry, u
 bool launch_nlm(const GeoK& g, const float* S, int first_target_row, int targets, float h,
                 float* Shat, cudaStream_t st);
 
+// sb_nlm3.cu (full paste blocks only; launch_nlm adds the tail kernel)
+bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int targets, float h,
+                 float* Shat, cudaStream_t st);
+
 // sb_gain.cu
 struct GainArgs {
   int frames;        // frames in this sub-call (M)

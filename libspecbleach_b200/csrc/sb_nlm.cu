@@ -674,13 +674,19 @@ bool launch_nlm(const GeoK& g, const float* S, int first_target_row, int targets
                 float* Shat, cudaStream_t st) {
   if (targets <= 0) return true;
   const int nfull = g.K / 8;
-  // SB_NLM_KERNEL=1 selects the direct-form kernel (reference accumulation order)
+  // SB_NLM_KERNEL=1: direct-form kernel (reference accumulation order); 2: row-SSD sharing
+  // with producer/reducer warps; default 3: sb_nlm3.cu
   static const int variant = [] {
     const char* e = getenv("SB_NLM_KERNEL");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 3;
   }();
   KTimer* kt = g_profile ? new KTimer(kcNlm, st) : nullptr;
-  if (nfull > 0 && variant == 2) {
+  if (nfull > 0 && variant == 3) {
+    if (!launch_nlm3(g, S, first_target_row, targets, h, Shat, st)) {
+      delete kt;
+      return false;
+    }
+  } else if (nfull > 0 && variant == 2) {
     static bool attr_set = false;
     if (!attr_set) {
       SB_CUDA(cudaFuncSetAttribute((const void*)nlm2_kernel,
