@@ -65,10 +65,15 @@ constexpr size_t SMEM3 = SMEM3_TILE + SMEM3_FLAGS + SMEM3_GATE + SMEM3_PRM;
 // tile-relative bin column -> float offset inside a staged row
 __device__ __forceinline__ int tcol3(int c_rel) { return SLOT3 * (c_rel >> 3) + (c_rel & 7); }
 
-// Units (dt + 16) in the order warps take them from the CTA's queue: the 7 wrapping dt
-// (~2.5 x the work of a plain one) first, so that the tail of the tile is made of short units.
-__constant__ signed char c_units3[NDT] = {0,  1,  2,  3,  18, 19, 20, 4,  5,  6, 7,
-                                          8,  9,  10, 11, 12, 13, 14, 15, 16, 17};
+// Units in the order warps take them from the CTA's queue: {dt + 16, half}.  half 0 = all
+// targets of the tile, 1 / 2 = first / second half.  The 7 wrapping dt (~2.5 x the work of a
+// plain one) go first, the last plain dt are split in two so that the tail of the tile is
+// made of short units.
+constexpr int NUNIT3 = 27;
+__constant__ signed char c_units3[NUNIT3][2] = {
+    {0, 0},  {1, 0},  {2, 0},  {3, 0},  {18, 0}, {19, 0}, {20, 0}, {4, 0},  {5, 0},
+    {6, 0},  {7, 0},  {8, 0},  {9, 0},  {10, 0}, {11, 0}, {12, 1}, {12, 2}, {13, 1},
+    {13, 2}, {14, 1}, {14, 2}, {15, 1}, {15, 2}, {16, 1}, {16, 2}, {17, 1}, {17, 2}};
 
 __device__ __forceinline__ float schraudolph_exp3(float x) {   // simd_utils.h:670-684
   if (x < -20.0f) return 0.0f;
@@ -92,7 +97,7 @@ struct Lane3 {
   unsigned* flags;        // flags of this lane's paste block: + tau * NB3 * FW3
   float* wout;            // weight scratch of this lane's paste block: + tau * wstride
   int wstride;            // floats between consecutive targets in the weight scratch
-  const unsigned* gate;
+  unsigned long long live;   // bit tau: this lane's paste block passes the energy gate at target tau
   int col_tg;             // float offset of bin bs inside a staged row
   int col_seg;            // float offset of the first partner bin of this lane
   int g;                  // df half: 0 -> df = -8 + c (c < 8), 1 -> df = c (c < 9)
@@ -171,14 +176,15 @@ __device__ __forceinline__ void emit_flags3(const Lane3& L, int tau, int dti, fl
   if (dti == kNlmPast && L.g == 1) d[0] = 3.0e38f;
   const float dmin = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])),
                            fminf(fminf(d[4], d[5]), fminf(fminf(d[6], d[7]), d[8])));
-  if (!(dmin > L.thr) && L.active && ((L.gate[tau] >> L.bl) & 1u))
+  if (!(dmin > L.thr) && ((L.live >> tau) & 1ull))
     emit_slow3(L.flags + (size_t)tau * (NB3 * FW3), L.wout + (size_t)tau * L.wstride,
                dti * 17 + 8 * L.g, L.g == 0 ? 0xffu : 0x1ffu, L.thr, L.inv, d[0], d[1], d[2], d[3],
                d[4], d[5], d[6], d[7], d[8]);
 }
 
 // ---- a dt that never wraps: delay-tree accumulation ----
-__device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int nT, bool edge) {
+// targets [ta, tb) of the tile: rows ta .. tb+6 are walked, the first 7 only fill the tree
+__device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int ta, int tb, bool edge) {
   const int dt = dti - kNlmPast;
   float R1[NC3], A[2][NC3], B[4][NC3];
 #pragma unroll
@@ -187,8 +193,8 @@ __device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int nT, boo
     A[0][c] = A[1][c] = 0.f;
     B[0][c] = B[1][c] = B[2][c] = B[3][c] = 0.f;
   }
-  const int steps = nT + 7;
-  for (int i0 = 0; i0 < steps; i0 += 4) {
+  const int steps = tb + 7;
+  for (int i0 = ta; i0 < steps; i0 += 4) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int i = i0 + u;
@@ -207,7 +213,7 @@ __device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int nT, boo
           B[u & 3][c] = b0;
         }
         const int tau = i - 7;
-        if (tau >= 0) emit_flags3(L, tau, dti, d, edge);
+        if (tau >= ta) emit_flags3(L, tau, dti, d, edge);
       }
     }
   }
@@ -217,7 +223,7 @@ __device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int nT, boo
 // age[r] = partial distance of the target whose patch row r is the current row.  Every step the
 // partial sums move one age up THROUGH the add (age[r] = age[r-1] + term, evaluated from r = 7
 // down), so the loop needs neither register rotation nor unrolling: r0+r1+...+r7 in order.
-__device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int nT, bool edge) {
+__device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int ta, int tb, bool edge) {
   const int dt = dti - kNlmPast;
   int rlo = 0, rhi = 8, shift = 0;                   // rows r < rlo or r >= rhi use the alias
   if (dt > 1) { rhi = 9 - dt; shift = -NDT; }        // dt = 2,3,4
@@ -227,9 +233,9 @@ __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int nT, bool
   for (int r = 0; r < 8; r++)
 #pragma unroll
     for (int c = 0; c < NC3; c++) age[r][c] = 0.f;
-  const int steps = nT + 7;
+  const int steps = tb + 7;
 #pragma unroll 1
-  for (int i = 0; i < steps; i++) {
+  for (int i = ta; i < steps; i++) {
     const int ra = 12 + i;
     float Rm[NC3], Rw[NC3];
     rowterms3(L, ra, ra + dt, Rm);
@@ -243,7 +249,7 @@ __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int nT, bool
 #pragma unroll
     for (int c = 0; c < NC3; c++) age[0][c] = (0 < rlo) ? Rw[c] : Rm[c];
     const int tau = i - 7;
-    if (tau >= 0) {
+    if (tau >= ta) {
       float d[NC3];
 #pragma unroll
       for (int c = 0; c < NC3; c++) d[c] = age[7][c];
@@ -311,11 +317,13 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
   {
     Lane3 L;
     L.tile = tile;
-    L.gate = gate;
     L.bl = lane >> 1;
     L.g = lane & 1;
     const int b = blk0 + L.bl;
     L.active = b < nfull;
+    L.live = 0ull;
+    if (L.active)
+      for (int t = 0; t < TT3; t++) L.live |= (unsigned long long)((gate[t] >> L.bl) & 1u) << t;
     L.flags = flags + L.bl * FW3;
     L.wstride = nfull * WPITCH3;
     L.wout = Wg + ((size_t)tau0 * nfull + (L.active ? b : 0)) * WPITCH3;
@@ -332,10 +340,14 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
       int u = 0;
       if (lane == 0) u = (int)atomicAdd(next_unit, 1u);
       u = __shfl_sync(0xffffffffu, u, 0);
-      if (u >= NDT) break;
-      const int dti = c_units3[u];
-      if (dti < 4 || dti > 17) walk_wrap3(L, dti, nT, edge);
-      else walk_plain3(L, dti, nT, edge);
+      if (u >= NUNIT3) break;
+      const int dti = c_units3[u][0], half = c_units3[u][1];
+      const int mid = (nT + 1) >> 1;
+      const int ta = half == 2 ? mid : 0;
+      const int tb = half == 1 ? mid : nT;
+      if (ta >= tb) continue;
+      if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
+      else walk_plain3(L, dti, ta, tb, edge);
     }
   }
   __syncthreads();
