@@ -270,6 +270,96 @@ def test_full_size_properties_config2(gpu, ref):
     assert float(np.mean(y[2 * sr:] ** 2)) < 0.96 * float(np.mean(x[2 * sr:] ** 2))  # test_audio_regression.c:237
 
 
+def _streams(count, seconds, sr, seed):
+    """`count` distinct mono streams built cheaply from a few synthesised ones (time shift + gain)."""
+    base = [synth(seconds + 1.0, sr, seed + i) for i in range(4)]
+    n = int(seconds * sr)
+    out = []
+    for i in range(count):
+        b = base[i % 4]
+        off = (37 * i) % sr
+        out.append(np.ascontiguousarray(b[off:off + n] * np.float32(0.6 + 0.4 * ((i * 7) % 11) / 10.0)))
+    return out
+
+
+def test_full_size_properties_config3(gpu, ref):
+    """BASELINE configs[2], one GPU's share at 8 GPUs: 512 independent 60 s mono streams,
+    2D NLM, through specbleach_b200_process_batch in waves of 128.  Anchors: (a) stream
+    independence -- every 64th stream equals the same stream processed on its own handle,
+    bit-exact; (b) one stream's 8 s prefix against the reference build; (c) finiteness."""
+    sr, secs, wave = 48000, 60.0, 128
+    checked = 0
+    for w0 in range(0, 512, wave):
+        xs = _streams(wave, secs, sr, 20260003 + w0)
+        ds = [gpu.Denoiser2D(sr, 50.0) for _ in xs]
+        ys = [np.empty_like(x) for x in xs]
+        for d in ds:
+            d.load_parameters(learn_noise=1)
+        assert gpu.process_batch(ds, [x[:sr] for x in xs], [y[:sr] for y in ys])
+        for d in ds:
+            d.load_parameters(**P2D)
+        assert gpu.process_batch(ds, [x[sr:] for x in xs], [y[sr:] for y in ys])
+        for d in ds:
+            d.close()
+        assert all(np.isfinite(y).all() for y in ys)
+        for i in range(0, wave, 64):
+            solo = run_flow(gpu.Denoiser2D(sr, 50.0), xs[i], sr, P2D, 1 << 19)
+            assert np.array_equal(solo, ys[i])
+            checked += 1
+        if w0 == 0:
+            n = 8 * sr
+            want = run_flow(ref.RefDenoiser(sr, 50.0, True), xs[5][:n], sr, P2D, 8192)
+            assert_parity(ys[5][:n], want, "config3 stream 5 prefix")
+    assert checked == 8
+
+
+def test_full_size_properties_config4(gpu, ref):
+    """BASELINE configs[3]: 1 h of non-stationary noise at 44.1 kHz, adaptive SPP-MMSE and
+    Martin (288 131 frames x 1504 bins through the per-bin sequential scans).  Anchors: the
+    first 10 s of the 1 h output are bit-identical to a 10 s run, which is checked against
+    the reference build; a second chunking gives the identical hour; finiteness."""
+    from libspecbleach_b200.synth import nonstationary_noise
+    sr = 44100
+    x = nonstationary_noise(3600.0, sr, 20260004)
+    for method in (0, 2):
+        prm = dict(P2D, adaptive_noise=1, noise_estimation_method=method)
+        y = run_flow(gpu.Denoiser2D(sr, 50.0), x, 0, prm, None)
+        assert np.all(np.isfinite(y))
+        n = 10 * sr
+        short = run_flow(gpu.Denoiser2D(sr, 50.0), x[:n], 0, prm, None)
+        assert np.array_equal(y[:n], short)
+        want = run_flow(ref.RefDenoiser(sr, 50.0, True), x[:n], 0, prm, None)
+        assert_parity(short, want, f"config4 method {method} prefix")
+        y2 = run_flow(gpu.Denoiser2D(sr, 50.0), x, 0, prm, 3_000_000)
+        assert np.array_equal(y, y2)
+
+
+def test_full_size_properties_config5(gpu, ref):
+    """BASELINE configs[4]: 96 kHz, 77 ms frames (fft 8192, 4097 bins), 8 channels x 120 s, 2D
+    with tonal reduction 12 dB, full masking protection and 100 % whitening, learned profile
+    with mains hum.  Anchors: channel independence (batch == solo, bit-exact), a 4 s prefix of
+    one channel against the reference build, finiteness."""
+    from libspecbleach_b200.synth import speech_plus_noise
+    sr, secs = 96000, 120.0
+    prm = dict(P2D, tonal_reduction=12.0, nlm_masking_protection=1.0, whitening_factor=100.0)
+    xs = [speech_plus_noise(secs, sr, 20260005 + c, hum_hz=60.0) for c in range(8)]
+    ds = [gpu.Denoiser2D(sr, 77.0) for _ in xs]
+    assert ds[0].profile_size() == 8192
+    ys = [np.empty_like(x) for x in xs]
+    for d in ds:
+        d.load_parameters(learn_noise=1)
+    assert gpu.process_batch(ds, [x[:sr] for x in xs], [y[:sr] for y in ys])
+    for d in ds:
+        d.load_parameters(**prm)
+    assert gpu.process_batch(ds, [x[sr:] for x in xs], [y[sr:] for y in ys])
+    assert all(np.isfinite(y).all() for y in ys)
+    solo = run_flow(gpu.Denoiser2D(sr, 77.0), xs[3], sr, prm, 1 << 20)
+    assert np.array_equal(solo, ys[3])
+    n = 4 * sr
+    want = run_flow(ref.RefDenoiser(sr, 77.0, True), xs[6][:n], sr, prm, 8192)
+    assert_parity(ys[6][:n], want, "config5 channel 6 prefix")
+
+
 def test_smoke_entry_point(gpu):
     import __graft_entry__ as ge
     ge.smoke()
