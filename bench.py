@@ -224,6 +224,9 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = api.lib()
+    if args.lanes or args.chunk_frames:
+        if not L.specbleach_b200_configure(args.chunk_frames or 4096, args.lanes or 4):
+            raise SystemExit("bench.py: specbleach_b200_configure failed: " + sb.last_error())
 
     chans = make_file(rank)
     n = chans[0].shape[0]
@@ -375,6 +378,8 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=11.0,
                     help="audio seconds per CPU worker per step in the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="engine lanes (0 = library default)")
+    ap.add_argument("--chunk-frames", type=int, default=0, help="frames per sub-call (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -358,33 +358,6 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
   }
 }
 
-// per-band forward-masking recursion, linear in u = T^0.6:
-//   T = (T_f^p + (T_prev*fwd)^p + (T_fut*bwd)^p)^(1/p)   (masking_estimator.c:270-288)
-__global__ void tscan_kernel(const GeoK g, int first_active, int active,
-                             const float* __restrict__ band_a, float* __restrict__ band_u,
-                             float* __restrict__ u_state) {
-  const int b = threadIdx.x;
-  if (b >= g.nb) return;
-  float u = u_state[b];
-  const float c = g.fwd_pow[b];
-  size_t o = (size_t)first_active * kBandPitch + b;
-  for (int f = 0; f < active; f += kScanBatch) {
-    float v[kScanBatch];
-#pragma unroll
-    for (int i = 0; i < kScanBatch; i++)
-      v[i] = (f + i < active) ? band_a[o + (size_t)i * kBandPitch] : 0.f;
-#pragma unroll
-    for (int i = 0; i < kScanBatch; i++) {
-      if (f + i < active) {
-        u = fmaf(c, u, v[i]);
-        band_u[o + (size_t)i * kBandPitch] = u;   // T = u^(1/0.6) is taken in nmr_kernel
-      }
-    }
-    o += (size_t)kScanBatch * kBandPitch;
-  }
-  u_state[b] = u;
-}
-
 // (frame, band): absolute-threshold floor, band NMR -> protection
 __global__ void __launch_bounds__(256)
 nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
@@ -418,28 +391,101 @@ nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
   }
 }
 
-// per-band protection EMA (spectral_smoother.c:213-223)
-__global__ void pscan_kernel(const GeoK g, int first_active, int active,
-                             float* __restrict__ band_p, float* __restrict__ p_state) {
-  const int b = threadIdx.x;
-  if (b >= g.nb) return;
-  float m = p_state[b];
-  size_t o = (size_t)first_active * kBandPitch + b;
-  for (int f = 0; f < active; f += kScanBatch) {
-    float v[kScanBatch];
-#pragma unroll
-    for (int i = 0; i < kScanBatch; i++)
-      v[i] = (f + i < active) ? band_p[o + (size_t)i * kBandPitch] : 0.f;
-#pragma unroll
-    for (int i = 0; i < kScanBatch; i++) {
-      if (f + i < active) {
-        m = (kVetoSmoothing * v[i]) + ((1.0f - kVetoSmoothing) * m);
-        band_p[o + (size_t)i * kBandPitch] = m;
+// ---------------------------------------------------------------------------
+// Sequential-in-time scans, staged through shared memory.
+//
+// The recursions above are strictly sequential over frames (and must stay so:
+// streaming invariance is bit-exact), independent over columns (bins / bands).
+// Walking global memory directly leaves one dependent ~1 us round trip per 16
+// frames on the critical path (305-360 us per 4096 frames, a third of a
+// sub-call's kernel time).  Here a CTA owns 32 columns: 7 mover warps stream
+// 32-frame tiles global -> shared with cp.async, four tiles ahead of the
+// scanner warp (lane = column), which runs the recurrence on shared memory in
+// place; the movers then write the finished tile back.  One barrier per tile.
+//   MODE 0: m = 0.5 v + 0.5 m   (bin EMA masking_veto.c:137-147, band EMA
+//           spectral_smoother.c:213-223), in place
+//   MODE 1: u = c[col] u + a    (forward masking, linear in u = T^0.6:
+//           T = (T_f^p + (T_prev*fwd)^p + (T_fut*bwd)^p)^(1/p), masking_estimator.c:270-288;
+//           T = u^(1/0.6) is taken in nmr_kernel), A -> B
+// ---------------------------------------------------------------------------
+constexpr int kRsTile = 32;      // frames per tile
+constexpr int kRsRing = 8;       // tiles resident in shared memory
+constexpr int kRsAhead = 5;      // prefetch distance (tiles)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct RsCoef { float c[32]; };   // MODE 1: per-column coefficient (one CTA, <= 32 bands)
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+rowscan_kernel(int ncols, int pitch, int rows, const float* A, float* B,   // B may alias A
+               const RsCoef coef, float* __restrict__ state) {
+  __shared__ float ring[kRsRing][kRsTile][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 32 + lane;
+  const bool cv = col < ncols;
+  const int ntiles = (rows + kRsTile - 1) / kRsTile;
+  constexpr int kMovers = 7;
+
+  // movers: rows of a tile are dealt round-robin to warps 1..7
+  auto load_tile = [&](int t) {
+    if (warp > 0 && t < ntiles) {
+      for (int r = warp - 1; r < kRsTile; r += kMovers) {
+        const int f = t * kRsTile + r;
+        if (f < rows && cv) cp_async4(&ring[t % kRsRing][r][lane], A + (size_t)f * pitch + col);
       }
     }
-    o += (size_t)kScanBatch * kBandPitch;
+    cp_async_commit();
+  };
+  float m = 0.f, c = 0.f;
+  if (warp == 0 && cv) {
+    m = state[col];
+    if (MODE == 1) c = coef.c[lane];
   }
-  p_state[b] = m;
+  for (int t = 0; t < kRsAhead; t++) load_tile(t);
+  for (int t = 0; t < ntiles; t++) {
+    // tile t has landed once at most kRsAhead-1 younger groups are pending
+    cp_async_wait<kRsAhead - 1>();
+    __syncthreads();
+    if (warp == 0) {
+      const int nr = (rows - t * kRsTile < kRsTile) ? rows - t * kRsTile : kRsTile;
+      float* tp = &ring[t % kRsRing][0][lane];
+#pragma unroll 8
+      for (int r = 0; r < nr; r++) {
+        const float v = tp[r * 32];
+        if (MODE == 0) m = (kVetoSmoothing * v) + ((1.0f - kVetoSmoothing) * m);
+        else m = fmaf(c, m, v);
+        tp[r * 32] = m;
+      }
+    } else {
+      // write back tile t-1 (finished in the previous iteration), then prefetch
+      if (t > 0) {
+        const int tb = t - 1;
+        for (int r = warp - 1; r < kRsTile; r += kMovers) {
+          const int f = tb * kRsTile + r;
+          if (f < rows && cv) B[(size_t)f * pitch + col] = ring[tb % kRsRing][r][lane];
+        }
+      }
+    }
+    load_tile(t + kRsAhead);
+  }
+  __syncthreads();
+  if (warp > 0 && ntiles > 0) {
+    const int tb = ntiles - 1;
+    for (int r = warp - 1; r < kRsTile; r += kMovers) {
+      const int f = tb * kRsTile + r;
+      if (f < rows && cv) B[(size_t)f * pitch + col] = ring[tb % kRsRing][r][lane];
+    }
+  }
+  if (warp == 0 && cv) state[col] = m;
 }
 
 // ---------------------------------------------------------------------------
@@ -622,9 +668,15 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
     if (use_veto || !a.two_d) {
       {
         KTimer kt_(kcBinScan, st);
-      bin_scan_kernel<<<(g.K + 127) / 128, 128, 0, st>>>(g, fa, active, a.two_d ? 1 : 0,
-                                                         a.smoothing, L.P, L.noise, L.Mg,
-                                                         L.stable, h.d_stable, h.d_sp_prev);
+      if (a.two_d) {
+        float* sp = L.stable + (size_t)fa * g.Kp;
+        rowscan_kernel<0><<<(g.K + 31) / 32, 256, 0, st>>>(g.K, g.Kp, active, sp, sp, RsCoef(),
+                                                           h.d_stable);
+      } else {
+        bin_scan_kernel<<<(g.K + 127) / 128, 128, 0, st>>>(g, fa, active, 0, a.smoothing, L.P,
+                                                           L.noise, L.Mg, L.stable, h.d_stable,
+                                                           h.d_sp_prev);
+      }
       SB_LAUNCH_CHECK();
       }
     }
@@ -637,8 +689,11 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
       }
       {
         KTimer kt_(kcTScan, st);
-      tscan_kernel<<<1, kBandPitch, 0, st>>>(g, fa, active, L.band_a, L.band_T,
-                                             h.d_band_state);
+      RsCoef fc;
+      for (int b = 0; b < 32; b++) fc.c[b] = b < g.nb ? g.fwd_pow[b] : 0.f;
+      rowscan_kernel<1><<<1, 256, 0, st>>>(g.nb, kBandPitch, active,
+                                           L.band_a + (size_t)fa * kBandPitch,
+                                           L.band_T + (size_t)fa * kBandPitch, fc, h.d_band_state);
       SB_LAUNCH_CHECK();
       }
       {
@@ -648,8 +703,10 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
       }
       {
         KTimer kt_(kcPScan, st);
-      pscan_kernel<<<1, kBandPitch, 0, st>>>(g, fa, active, L.band_p,
-                                             h.d_band_state + kBandPitch);
+      rowscan_kernel<0><<<1, 256, 0, st>>>(g.nb, kBandPitch, active,
+                                           L.band_p + (size_t)fa * kBandPitch,
+                                           L.band_p + (size_t)fa * kBandPitch, RsCoef(),
+                                           h.d_band_state + kBandPitch);
       SB_LAUNCH_CHECK();
       }
     }
