@@ -60,6 +60,41 @@ bool specbleach_b200_process_batch_device(SpectralBleachHandle* instances, uint3
                                           const float* const* d_inputs,
                                           float* const* d_outputs);
 
+/* Noise-profile persistence ------------------------------------------------
+ * The reference can only hand out / take in raw profile arrays
+ * (specbleach_2d_denoiser.c:145-206: get_noise_profile_for_mode,
+ * load_noise_profile_for_mode).  These two wrap them in a small checksummed file
+ * ("SBNP" v1: sample rate, frame size, denoiser kind, and for each of the four
+ * modes block count, availability and the array) so that one learned profile can
+ * be shared by thousands of stream handles.  load fails (false, last_error set)
+ * when the file was saved for another (sample_rate, frame_ms, 1D/2D). */
+bool specbleach_b200_profile_save(SpectralBleachHandle instance, const char* path);
+bool specbleach_b200_profile_load(SpectralBleachHandle instance, const char* path);
+
+/* Streaming-state snapshot: parameters, profiles, FIFO / overlap-add tails,
+ * 2D delay line and NLM ring, veto recursions, estimator state -- everything a
+ * handle carries between process() calls -- as one opaque,
+ * checksummed host blob.  A handle of the same geometry restored from it (on any
+ * GPU / process) continues the stream bit-exactly. */
+size_t specbleach_b200_state_size(SpectralBleachHandle instance);
+bool specbleach_b200_state_save(SpectralBleachHandle instance, void* blob, size_t bytes);
+bool specbleach_b200_state_load(SpectralBleachHandle instance, const void* blob, size_t bytes);
+
+/* Interleaved multichannel PCM through one handle per channel: replaces the
+ * host-side de-interleave / sf_readf_float / sf_writef_float loop of
+ * examples/denoiser_demo.c:217-300.  `input` / `output` are HOST buffers of
+ * frames * channels samples (may alias); conversion and (de)interleaving run on
+ * the device, the channels as one batch. */
+enum {
+  SPECBLEACH_B200_PCM_F32 = 0, /* IEEE float, as is                           */
+  SPECBLEACH_B200_PCM_S16 = 1, /* in: x / 2^15; out: round(x * (2^15-1)), sat. */
+  SPECBLEACH_B200_PCM_S24 = 2, /* packed 3-byte little endian                  */
+  SPECBLEACH_B200_PCM_S32 = 3
+};
+bool specbleach_b200_process_interleaved(SpectralBleachHandle* instances, uint32_t channels,
+                                         uint32_t frames, int format, const void* input,
+                                         void* output);
+
 /* Instrumentation ---------------------------------------------------------- */
 typedef struct SpecbleachB200Stats {
   uint64_t kernel_launches;    /* kernels launched by this library since reset      */

@@ -63,7 +63,9 @@ PUBLIC_SYMBOLS = [pre + n for pre in ("specbleach_", "specbleach_2d_") for n in 
 EXTENSION_SYMBOLS = ["specbleach_b200_" + n for n in (
     "device_count", "set_device", "last_error", "host_alloc", "host_free", "configure",
     "process_device", "process_batch", "process_batch_device", "profile", "stats_reset",
-    "stats_get", "stats_classes", "stats_class_name", "stats_class", "get_geometry", "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft")]
+    "stats_get", "stats_classes", "stats_class_name", "stats_class", "get_geometry",
+    "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft", "profile_save", "profile_load",
+    "state_size", "state_save", "state_load", "process_interleaved")]
 
 
 def lib():
@@ -128,6 +130,19 @@ def lib():
     L.specbleach_b200_stats_class_name.argtypes = [C.c_int]
     L.specbleach_b200_stats_class.restype = C.c_bool
     L.specbleach_b200_stats_class.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.specbleach_b200_profile_save.restype = C.c_bool
+    L.specbleach_b200_profile_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.specbleach_b200_profile_load.restype = C.c_bool
+    L.specbleach_b200_profile_load.argtypes = [C.c_void_p, C.c_char_p]
+    L.specbleach_b200_state_size.restype = C.c_size_t
+    L.specbleach_b200_state_size.argtypes = [C.c_void_p]
+    L.specbleach_b200_state_save.restype = C.c_bool
+    L.specbleach_b200_state_save.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.specbleach_b200_state_load.restype = C.c_bool
+    L.specbleach_b200_state_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.specbleach_b200_process_interleaved.restype = C.c_bool
+    L.specbleach_b200_process_interleaved.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32,
+                                                      C.c_int, C.c_void_p, C.c_void_p]
     L.specbleach_b200_get_geometry.restype = C.c_bool
     L.specbleach_b200_get_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
     L.specbleach_b200_debug_fp32_peak_tflops.restype = C.c_double
@@ -264,6 +279,23 @@ class Denoiser:
     def reset_profile(self) -> bool:
         return bool(self._f("reset_noise_profile")(self.h))
 
+    # ---- extensions: persistence (include/specbleach_b200.h) ----
+    def save_profile(self, path) -> bool:
+        return bool(self.L.specbleach_b200_profile_save(self.h, str(path).encode()))
+
+    def restore_profile(self, path) -> bool:
+        return bool(self.L.specbleach_b200_profile_load(self.h, str(path).encode()))
+
+    def save_state(self) -> bytes:
+        n = int(self.L.specbleach_b200_state_size(self.h))
+        buf = C.create_string_buffer(n)
+        if not self.L.specbleach_b200_state_save(self.h, buf, n):
+            raise RuntimeError("state_save failed: " + last_error())
+        return buf.raw
+
+    def load_state(self, blob: bytes) -> bool:
+        return bool(self.L.specbleach_b200_state_load(self.h, blob, len(blob)))
+
     def geometry(self) -> dict:
         v = [C.c_uint32() for _ in range(4)]
         self.L.specbleach_b200_get_geometry(self.h, *[C.byref(a) for a in v])
@@ -299,6 +331,24 @@ def process_batch(denoisers, inputs, outputs, device: bool = False) -> bool:
         outs = (C.c_void_p * cnt)(*[a.ctypes.data for a in outputs])
         ok = L.specbleach_b200_process_batch(hs, cnt, ns, ins, outs)
     return bool(ok)
+
+
+PCM_FORMATS = {"f32": 0, "s16": 1, "s24": 2, "s32": 3}
+
+
+def process_interleaved(denoisers, pcm: np.ndarray, fmt: str) -> np.ndarray:
+    """specbleach_b200_process_interleaved: ``pcm`` is [frames, channels] (float32, int16,
+    int32) or, for "s24", a uint8 array of frames*channels*3 packed bytes."""
+    L = lib()
+    ch = len(denoisers)
+    pcm = np.ascontiguousarray(pcm)
+    frames = pcm.size // (3 * ch) if fmt == "s24" else pcm.shape[0]
+    out = np.empty_like(pcm)
+    hs = (C.c_void_p * ch)(*[d.h for d in denoisers])
+    if not L.specbleach_b200_process_interleaved(hs, ch, frames, PCM_FORMATS[fmt], pcm.ctypes.data,
+                                                 out.ctypes.data):
+        raise RuntimeError("process_interleaved failed: " + last_error())
+    return out
 
 
 def debug_nlm(snr: np.ndarray, h: float = 1.0) -> np.ndarray:

@@ -93,3 +93,22 @@ def test_product_never_imports_the_oracle():
     pat = re.compile(r"(from\s+oracle|import\s+oracle|oracle/|specbleach_np|ref_binding|libspecbleach_ref)")
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")):
         assert not pat.search(f.read_text()), f
+
+
+def test_extension_io_entry_points_reject_bad_arguments_without_a_gpu(tmp_path):
+    """persistence / PCM front end (include/specbleach_b200.h): NULL handles and buffers."""
+    from libspecbleach_b200 import api
+    L = api.lib()
+    assert not L.specbleach_b200_profile_save(None, str(tmp_path / "x").encode())
+    assert not L.specbleach_b200_profile_load(None, str(tmp_path / "x").encode())
+    assert L.specbleach_b200_state_size(None) == 0
+    assert not L.specbleach_b200_state_save(None, None, 0)
+    assert not L.specbleach_b200_state_load(None, None, 0)
+    assert not L.specbleach_b200_process_interleaved(None, 2, 16, 0, None, None)
+
+
+def test_wav_tool_is_built_and_prints_usage():
+    tool = ROOT / "tools" / "sb_denoise"
+    assert tool.exists(), "run __graft_entry__.build()"
+    r = subprocess.run([str(tool)], capture_output=True, text=True)
+    assert r.returncode == 2 and "Usage" in r.stderr

@@ -1,0 +1,157 @@
+"""GPU tests of the steps on either side of the hot path:
+noise-profile persistence, streaming-state snapshot, interleaved PCM front end and the
+WAV command-line tool.  Reference behaviour they are held to: get/load profile round trip
+(specbleach_2d_denoiser.c:145-206), streaming invariance (stft_processor.c:134) and
+libsndfile's sample conversions as used by examples/denoiser_demo.c:217-300."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from common import P1D, P2D, assert_parity, run_flow
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def synth(seconds, sr, seed):
+    from libspecbleach_b200.synth import speech_plus_noise
+    return speech_plus_noise(seconds, sr, seed)
+
+
+def test_profile_file_round_trip(gpu, tmp_path):
+    """a profile learned on one handle, saved, and restored into fresh handles gives the
+    same output as learning in place; wrong geometry / corrupt files are refused."""
+    sr = 48000
+    x = synth(4.0, sr, 21)
+    a = gpu.Denoiser2D(sr, 50.0)
+    a.load_parameters(learn_noise=1)
+    a.process(x[:sr])
+    a.load_parameters(**P2D)
+    ya = a.process(x[sr:])                     # finalises the profiles, then denoises
+    f = tmp_path / "noise.sbnp"
+    assert a.save_profile(f)
+    b = gpu.Denoiser2D(sr, 50.0)
+    assert b.restore_profile(f)
+    for m in (1, 2, 3, 4):
+        assert np.array_equal(a.get_profile(m), b.get_profile(m))
+        assert a.block_count(m) == b.block_count(m) and a.profile_available(m) == b.profile_available(m)
+    b.load_parameters(**P2D)
+    yb = b.process(x[sr:])
+    c = gpu.Denoiser2D(sr, 50.0)               # the reference's own way: load_noise_profile_for_mode
+    for m in (1, 2, 3, 4):
+        assert c.load_profile(a.get_profile(m), a.block_count(m), m)
+    c.load_parameters(**P2D)
+    assert np.array_equal(yb, c.process(x[sr:]))
+    # same profile, same input: once the stream history has flushed the outputs agree
+    assert np.max(np.abs(ya[sr:] - yb[sr:])) <= 1e-5
+    assert not gpu.Denoiser2D(44100, 50.0).restore_profile(f)          # other geometry
+    assert not gpu.Denoiser1D(sr, 50.0).restore_profile(f)             # other denoiser
+    raw = bytearray(f.read_bytes())
+    raw[200] ^= 0x40
+    g = tmp_path / "bad.sbnp"
+    g.write_bytes(bytes(raw))
+    assert not gpu.Denoiser2D(sr, 50.0).restore_profile(g)             # checksum
+    assert not gpu.Denoiser2D(sr, 50.0).restore_profile(tmp_path / "missing.sbnp")
+
+
+@pytest.mark.parametrize("two_d,prm", [(True, P2D), (False, P1D),
+                                       (True, dict(P2D, adaptive_noise=1, noise_estimation_method=2)),
+                                       (True, dict(P2D, adaptive_noise=1, noise_estimation_method=1))],
+                         ids=["2d", "1d", "2d_martin", "2d_brandt"])
+def test_state_snapshot_resumes_bit_exact(gpu, two_d, prm):
+    """stop a stream mid-way (not on a hop boundary), snapshot, restore into a NEW handle and
+    continue: identical to the uninterrupted run."""
+    sr = 48000
+    x = synth(6.0, sr, 33)
+    cut = 3 * sr + 777
+    full = run_flow(gpu.Denoiser(sr, 50.0, two_d), x, sr, prm, None)
+    a = gpu.Denoiser(sr, 50.0, two_d)
+    a.load_parameters(learn_noise=1)
+    y0 = a.process(x[:sr])
+    a.load_parameters(**prm)
+    y1 = a.process(x[sr:cut])
+    blob = a.save_state()
+    a.close()
+    b = gpu.Denoiser(sr, 50.0, two_d)
+    assert b.load_state(blob)
+    y2 = b.process(x[cut:])
+    assert np.array_equal(full, np.concatenate([y0, y1, y2]))
+    assert not gpu.Denoiser(44100, 50.0, two_d).load_state(blob)
+    assert not b.load_state(blob[:-5] + b"12345")
+
+
+@pytest.mark.parametrize("fmt", ["f32", "s16", "s24", "s32"])
+def test_interleaved_pcm_equals_per_channel(gpu, fmt):
+    """3 interleaved channels through specbleach_b200_process_interleaved == converting on the
+    host the way libsndfile does and calling specbleach_2d_process per channel."""
+    from libspecbleach_b200 import api
+    sr, ch = 48000, 3
+    xs = np.stack([synth(3.0, sr, 40 + c) for c in range(ch)], axis=1)      # [frames, ch]
+    if fmt == "f32":
+        pcm, xf = xs.copy(), xs
+    elif fmt == "s16":
+        pcm = np.round(xs * 32767.0).astype(np.int16)
+        xf = (pcm.astype(np.float32) / np.float32(32768.0))
+    elif fmt == "s32":
+        pcm = np.round(xs.astype(np.float64) * 2147483647.0).astype(np.int32)
+        xf = (pcm.astype(np.float64) / 2147483648.0).astype(np.float32)
+    else:
+        q = np.round(xs.astype(np.float64) * 8388607.0).astype(np.int32)
+        b = q.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3]
+        pcm = np.ascontiguousarray(b).reshape(-1)
+        xf = (q.astype(np.float64) / 8388608.0).astype(np.float32)
+    ds = [gpu.Denoiser2D(sr, 50.0) for _ in range(ch)]
+    for d in ds:
+        d.load_parameters(learn_noise=1)
+    n0 = sr * ch * 3 if fmt == "s24" else sr
+    head = api.process_interleaved(ds, pcm[:n0], fmt)
+    for d in ds:
+        d.load_parameters(**P2D)
+    tail = api.process_interleaved(ds, pcm[n0:], fmt)
+    got = np.concatenate([head, tail])
+    want = np.stack([run_flow(gpu.Denoiser2D(sr, 50.0), np.ascontiguousarray(xf[:, c]), sr, P2D, None)
+                     for c in range(ch)], axis=1)
+    if fmt == "f32":
+        assert np.array_equal(got, want)
+    elif fmt == "s16":
+        assert np.array_equal(got, np.clip(np.rint(want * np.float32(32767.0)), -32768, 32767).astype(np.int16))
+    elif fmt == "s32":
+        ref = np.clip(np.rint(want.astype(np.float64) * 2147483647.0), -2147483648.0, 2147483647.0)
+        assert np.array_equal(got, ref.astype(np.int32))
+    else:
+        ref = np.clip(np.rint(want * np.float32(8388607.0)), -8388608, 8388607).astype("<i4")
+        assert np.array_equal(got, np.ascontiguousarray(ref.view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1))
+
+
+def test_wav_tool_matches_api_and_reference(gpu, ref, tmp_path):
+    """tools/sb_denoise on a stereo 16-bit WAV: the output file equals the API path, and its
+    left channel is within tolerance of the reference build fed the same decoded samples."""
+    from scipy.io import wavfile
+    tool = ROOT / "tools" / "sb_denoise"
+    if not tool.exists():
+        pytest.fail("tools/sb_denoise not built (python -c 'import __graft_entry__ as g; g.build()')")
+    sr = 44100
+    xs = np.stack([synth(4.0, sr, 50 + c) for c in range(2)], axis=1)
+    pcm = np.round(xs * 32767.0).astype(np.int16)
+    fin, fout, fprof = tmp_path / "in.wav", tmp_path / "out.wav", tmp_path / "p.sbnp"
+    wavfile.write(fin, sr, pcm)
+    r = subprocess.run([str(tool), "--learn-seconds", "1.0", "--tonal", "6", "--save-profile", str(fprof),
+                        str(fin), str(fout)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sr2, got = wavfile.read(fout)
+    assert sr2 == sr and got.shape == pcm.shape and got.dtype == np.int16
+    xf = pcm.astype(np.float32) / np.float32(32768.0)
+    want = run_flow(ref.RefDenoiser(sr, 50.0, True), np.ascontiguousarray(xf[:, 0]), sr, P2D, 8192)
+    assert_parity(got[:, 0].astype(np.float32) / np.float32(32767.0), want, "wav tool, left channel",
+                  max_abs=1e-4 + 1.0 / 32767.0, snr_db=60.0)     # + 16-bit quantisation
+    # the saved profile drives a second run without a learn pass
+    fout2 = tmp_path / "out2.wav"
+    r = subprocess.run([str(tool), "--load-profile", str(fprof), "--tonal", "6", str(fin), str(fout2)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert wavfile.read(fout2)[1].shape == pcm.shape
+    bad = subprocess.run([str(tool), str(tmp_path / "nope.wav"), str(fout)], capture_output=True, text=True)
+    assert bad.returncode != 0
