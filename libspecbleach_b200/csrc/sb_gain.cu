@@ -68,47 +68,78 @@ __global__ void snr_kernel(const GeoK g, const float* __restrict__ P,
   S[o] = v;
 }
 
-// 51-bin edge-clamped median over frequency, then the tonal mask.
-// grid = (bin tiles of 256, rows); each CTA stages its bins plus a 25-bin halo.
-__global__ void __launch_bounds__(256)
+// 51-bin edge-clamped median over frequency, then the tonal mask
+// (tonal_detector.c:24-162).  A thread walks a segment of 32 consecutive bins of one
+// row and keeps the 51-value window SORTED in shared memory (column layout, conflict
+// free): the first window is insertion-sorted, every next one replaces the value that
+// leaves by the value that enters with one shifting pass, so a bin costs O(51) instead
+// of the O(51^2) of a selection per bin (3.4 ms -> 0.1 ms per 4800 frames when the
+// noise estimate changes every frame).  median = sorted[25].
+constexpr int kTmSeg = 32;       // bins per thread
+constexpr int kTmThreads = 128;
+
+__global__ void __launch_bounds__(kTmThreads)
 tonal_mask_kernel(const GeoK g, const float* __restrict__ det, int det_stride,
-                  float* __restrict__ mask, int mask_stride) {
-  __shared__ float sm[256 + kTonalWindow];
-  const int row = blockIdx.y;
+                  float* __restrict__ mask, int mask_stride, int rows, int segs) {
+  __shared__ float win[kTonalWindow][kTmThreads];
+  const int id = blockIdx.x * kTmThreads + threadIdx.x;
+  if (id >= rows * segs) return;
+  const int row = id / segs;
+  const int k0 = (id - row * segs) * kTmSeg;
   const float* __restrict__ d = det + (size_t)row * det_stride;
+  float* __restrict__ mo = mask + (size_t)row * mask_stride;
   const int half = kTonalWindow / 2;
   const int K = g.K;
-  const int k0 = blockIdx.x * 256;
-  for (int e = threadIdx.x; e < 256 + 2 * half; e += blockDim.x) {
-    int idx = k0 + e - half;
-    idx = idx < 0 ? 0 : (idx > K - 1 ? K - 1 : idx);
-    sm[e] = d[idx];
+  const int t = threadIdx.x;
+  auto at = [&](int idx) { return __ldg(&d[idx < 0 ? 0 : (idx > K - 1 ? K - 1 : idx)]); };
+  // insertion sort of the first window: bins k0-25 .. k0+25 (clamped)
+  for (int i = 0; i < kTonalWindow; i++) {
+    const float v = at(k0 - half + i);
+    int p = i;
+    while (p > 0 && win[p - 1][t] > v) {
+      win[p][t] = win[p - 1][t];
+      p--;
+    }
+    win[p][t] = v;
   }
-  __syncthreads();
-  const int k = k0 + threadIdx.x;
-  if (k >= g.Kp) return;
-  float m = 0.f;
-  if (k < K) {
-    const float* w = &sm[threadIdx.x];   // window = w[0..50]
-    float med = w[half];
-    for (int i = 0; i < kTonalWindow; i++) {
-      const float v = w[i];
-      int less = 0, leq = 0;
-#pragma unroll
-      for (int j = 0; j < kTonalWindow; j++) {
-        const float u = w[j];
-        less += (u < v);
-        leq += (u <= v);
+  const int kend = (k0 + kTmSeg < g.Kp) ? k0 + kTmSeg : g.Kp;
+  for (int k = k0; k < kend; k++) {
+    float m = 0.f;
+    if (k < K) {
+      const float med = win[half][t];
+      const float peak = at(k);
+      if (!(peak - med < kMinPeakProminence)) {
+        const float ratio = peak / (med + 1e-20f);
+        if (ratio > kPeakThreshold) m = (peak - med) / (peak + 1e-20f);
       }
-      if (less <= half && half < leq) { med = v; break; }
     }
-    const float peak = w[half];
-    if (!(peak - med < kMinPeakProminence)) {
-      const float ratio = peak / (med + 1e-20f);
-      if (ratio > kPeakThreshold) m = (peak - med) / (peak + 1e-20f);
+    mo[k] = m;
+    if (k + 1 < kend && k + 1 < K) {
+      // slide: bin k-25 leaves, bin k+26 enters
+      const float old = at(k - half), nw = at(k + 1 + half);
+      if (old != nw) {
+        int lo = 0, hi = kTonalWindow - 1;           // first position holding `old`
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (win[mid][t] < old) lo = mid + 1;
+          else hi = mid;
+        }
+        int p = lo;
+        if (nw > old) {
+          while (p < kTonalWindow - 1 && win[p + 1][t] < nw) {
+            win[p][t] = win[p + 1][t];
+            p++;
+          }
+        } else {
+          while (p > 0 && win[p - 1][t] > nw) {
+            win[p][t] = win[p - 1][t];
+            p--;
+          }
+        }
+        win[p][t] = nw;
+      }
     }
   }
-  mask[(size_t)row * mask_stride + k] = m;
 }
 
 // Whitening weights: smooth3(noise) -> median (bitonic sort) -> power-law weights.
@@ -620,8 +651,9 @@ bool launch_tonal_mask(const GeoK& g, const float* det, int det_stride, int rows
                        cudaStream_t st) {
   KTimer kt_(kcTonal, st);
   if (rows <= 0) return true;
-  dim3 grid((g.Kp + 255) / 256, rows);
-  tonal_mask_kernel<<<grid, 256, 0, st>>>(g, det, det_stride, mask, g.Kp);
+  const int segs = (g.Kp + kTmSeg - 1) / kTmSeg;
+  const int blocks = (rows * segs + kTmThreads - 1) / kTmThreads;
+  tonal_mask_kernel<<<blocks, kTmThreads, 0, st>>>(g, det, det_stride, mask, g.Kp, rows, segs);
   SB_LAUNCH_CHECK();
   return true;
 }
