@@ -60,3 +60,16 @@ def test_two_ranks_gloo():
     assert [(r[1], r[2]) for r in res] == [(0, 4), (4, 7)]
     for r in res:   # 420 s of audio / max(100, 200) ms
         assert abs(r[3] - 420.0 / 0.2) < 1e-6 and abs(r[4] - 200.0) < 1e-9
+
+
+def test_time_tiles_cover_the_stream_on_hop_boundaries():
+    from libspecbleach_b200.sharding import time_tiles
+    n, hop, first = 48000 * 30 + 123, 600, 48000
+    for tiles in (1, 2, 3, 8):
+        plan = time_tiles(n, hop, tiles, 512, first)
+        assert plan[0][0] == plan[0][1] == first and plan[-1][2] == n
+        for (i0, a0, b0), (i1, a1, b1) in zip(plan, plan[1:]):
+            assert b0 == a1 and (a1 - first) % hop == 0 and (i1 - first) % hop == 0
+            assert i1 == max(first, a1 - 512 * hop)
+    with pytest.raises(ValueError):
+        time_tiles(100, 0, 1)
