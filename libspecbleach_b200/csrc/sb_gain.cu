@@ -142,6 +142,50 @@ tonal_mask_kernel(const GeoK g, const float* __restrict__ det, int det_stride,
   }
 }
 
+// Few rows (the static manual profile: one row per parameter change): selection per bin,
+// one thread per bin -- more parallel than the sliding window when there is little to do.
+// grid = (bin tiles of 256, rows); each CTA stages its bins plus a 25-bin halo.
+__global__ void __launch_bounds__(256)
+tonal_mask_direct_kernel(const GeoK g, const float* __restrict__ det, int det_stride,
+                  float* __restrict__ mask, int mask_stride) {
+  __shared__ float sm[256 + kTonalWindow];
+  const int row = blockIdx.y;
+  const float* __restrict__ d = det + (size_t)row * det_stride;
+  const int half = kTonalWindow / 2;
+  const int K = g.K;
+  const int k0 = blockIdx.x * 256;
+  for (int e = threadIdx.x; e < 256 + 2 * half; e += blockDim.x) {
+    int idx = k0 + e - half;
+    idx = idx < 0 ? 0 : (idx > K - 1 ? K - 1 : idx);
+    sm[e] = d[idx];
+  }
+  __syncthreads();
+  const int k = k0 + threadIdx.x;
+  if (k >= g.Kp) return;
+  float m = 0.f;
+  if (k < K) {
+    const float* w = &sm[threadIdx.x];   // window = w[0..50]
+    float med = w[half];
+    for (int i = 0; i < kTonalWindow; i++) {
+      const float v = w[i];
+      int less = 0, leq = 0;
+#pragma unroll
+      for (int j = 0; j < kTonalWindow; j++) {
+        const float u = w[j];
+        less += (u < v);
+        leq += (u <= v);
+      }
+      if (less <= half && half < leq) { med = v; break; }
+    }
+    const float peak = w[half];
+    if (!(peak - med < kMinPeakProminence)) {
+      const float ratio = peak / (med + 1e-20f);
+      if (ratio > kPeakThreshold) m = (peak - med) / (peak + 1e-20f);
+    }
+  }
+  mask[(size_t)row * mask_stride + k] = m;
+}
+
 // Whitening weights: smooth3(noise) -> median (bitonic sort) -> power-law weights.
 __global__ void __launch_bounds__(512)
 whitening_kernel(const GeoK g, const float* __restrict__ noise, int noise_stride, float whit,
@@ -651,6 +695,12 @@ bool launch_tonal_mask(const GeoK& g, const float* det, int det_stride, int rows
                        cudaStream_t st) {
   KTimer kt_(kcTonal, st);
   if (rows <= 0) return true;
+  if (rows < 32) {
+    dim3 grid((g.Kp + 255) / 256, rows);
+    tonal_mask_direct_kernel<<<grid, 256, 0, st>>>(g, det, det_stride, mask, g.Kp);
+    SB_LAUNCH_CHECK();
+    return true;
+  }
   const int segs = (g.Kp + kTmSeg - 1) / kTmSeg;
   const int blocks = (rows * segs + kTmThreads - 1) / kTmThreads;
   tonal_mask_kernel<<<blocks, kTmThreads, 0, st>>>(g, det, det_stride, mask, g.Kp, rows, segs);

@@ -9,8 +9,8 @@
 //
 // FFT: one CTA per frame.  The N real samples are packed into M = N/2 complex
 // points, transformed by a mixed-radix Stockham autosort FFT that ping-pongs
-// between two shared-memory buffers (radix 4 and 2 hard-wired, any other prime
-// factor through a generic O(r) per output butterfly), and split into the
+// between two shared-memory buffers (radix 4, 2, 5 and 3 hard-wired, any other
+// prime factor through a generic O(r) per output butterfly in double), and split into the
 // N/2+1 bins of the real transform.  The frame sizes of the library are not
 // powers of two (N = frame + 800), hence the runtime factor list.
 #include "sb_common.h"
@@ -71,6 +71,58 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
         if (INV) w1.y = -w1.y;
         y[q + s * (2 * j)] = cadd(a, b);
         y[q + s * (2 * j + 1)] = cmul(csub(a, b), w1);
+      }
+    } else if (r == 5) {
+      // 5-point DFT from the symmetric / antisymmetric pairs (x1 +- x4, x2 +- x3)
+      const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
+      const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
+      for (int idx = threadIdx.x; idx < M / 5; idx += blockDim.x) {
+        const int j = idx / s;
+        const int q = idx - j * s;
+        const float2 x0 = x[q + s * j];
+        const float2 x1 = x[q + s * (j + l)];
+        const float2 x2 = x[q + s * (j + 2 * l)];
+        const float2 x3 = x[q + s * (j + 3 * l)];
+        const float2 x4 = x[q + s * (j + 4 * l)];
+        const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+        const float2 a1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+        const float2 a2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+        const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        // forward: y1 = a1 - i b1, y4 = a1 + i b1, y2 = a2 - i b2, y3 = a2 + i b2; inverse: conjugate roots
+        const float2 ib1 = INV ? make_float2(-b1.y, b1.x) : make_float2(b1.y, -b1.x);
+        const float2 ib2 = INV ? make_float2(-b2.y, b2.x) : make_float2(b2.y, -b2.x);
+        float2 w1 = __ldg(&tw[j * tstep]);
+        float2 w2 = __ldg(&tw[2 * j * tstep]);
+        float2 w3 = __ldg(&tw[3 * j * tstep]);
+        float2 w4 = __ldg(&tw[4 * j * tstep]);
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
+        float2* o = &y[q + s * (5 * j)];
+        o[0] = cadd(x0, cadd(t1, t2));
+        o[s] = cmul(cadd(a1, ib1), w1);
+        o[2 * s] = cmul(cadd(a2, ib2), w2);
+        o[3 * s] = cmul(csub(a2, ib2), w3);
+        o[4 * s] = cmul(csub(a1, ib1), w4);
+      }
+    } else if (r == 3) {
+      const float h3 = 0.86602540378443865f;   // sin(2pi/3)
+      for (int idx = threadIdx.x; idx < M / 3; idx += blockDim.x) {
+        const int j = idx / s;
+        const int q = idx - j * s;
+        const float2 x0 = x[q + s * j];
+        const float2 x1 = x[q + s * (j + l)];
+        const float2 x2 = x[q + s * (j + 2 * l)];
+        const float2 t1 = cadd(x1, x2), t3 = csub(x1, x2);
+        const float2 a = make_float2(x0.x - 0.5f * t1.x, x0.y - 0.5f * t1.y);
+        const float2 b = make_float2(h3 * t3.x, h3 * t3.y);
+        const float2 ib = INV ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
+        float2 w1 = __ldg(&tw[j * tstep]);
+        float2 w2 = __ldg(&tw[2 * j * tstep]);
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
+        float2* o = &y[q + s * (3 * j)];
+        o[0] = cadd(x0, t1);
+        o[s] = cmul(cadd(a, ib), w1);
+        o[2 * s] = cmul(csub(a, ib), w2);
       }
     } else {
       // generic radix: one work item per output point; the r-term sum runs in
