@@ -289,20 +289,34 @@ nlm_tail_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int f
     wgt[threadIdx.x] = w;
   }
   __syncthreads();
+  // compact the (few) non-zero weights, keeping the reference's flat (dt, df) order
+  __shared__ unsigned short live_idx[NDT * 17];
+  __shared__ int n_live;
+  if (threadIdx.x < 32) {
+    int base = 0;
+    for (int c0 = 0; c0 < NDT * 17; c0 += 32) {
+      const int c = c0 + threadIdx.x;
+      const bool on = c < NDT * 17 && wgt[c] > 0.0f;
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) live_idx[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned short)c;
+      base += __popc(m);
+    }
+    if (threadIdx.x == 0) n_live = base;
+  }
+  __syncthreads();
   if (threadIdx.x < lim) {
     const int i = threadIdx.x;
     float acc = 0.0f, ws = 0.0f;
-    for (int dti = 0; dti < NDT; dti++) {
-      const float* cr = tile[dti];   // frame t+dt, dt = dti-16, never wraps
-      for (int dfi = 0; dfi < 17; dfi++) {
-        const float w = wgt[dti * 17 + dfi];
-        if (w > 0.0f) {
-          int cb = bs + i + dfi - kNlmRangeFreq;
-          cb = cb < 0 ? 0 : (cb > K - 1 ? K - 1 : cb);
-          acc = fmaf(w, cr[cb - c_origin], acc);
-          ws += w;
-        }
-      }
+    const int n = n_live;
+    for (int e = 0; e < n; e++) {
+      const int c = live_idx[e];
+      const int dti = c / 17;
+      const int dfi = c - dti * 17;
+      const float w = wgt[c];
+      int cb = bs + i + dfi - kNlmRangeFreq;
+      cb = cb < 0 ? 0 : (cb > K - 1 ? K - 1 : cb);
+      acc = fmaf(w, tile[dti][cb - c_origin], acc);   // frame t+dt, dt = dti-16, never wraps
+      ws += w;
     }
     const float tv = tile[kNlmPast][bs + i - c_origin];
     out[(size_t)target * pitchO + bs + i] = (ws > kNlmMinWeight) ? acc / ws : tv;

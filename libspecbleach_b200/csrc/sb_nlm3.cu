@@ -48,7 +48,6 @@ constexpr int GRP3 = NB3 + 2;               // 8-bin column groups per row: bins
 constexpr int SLOT3 = 12;                   // floats per column group: consecutive paste blocks are
                                             // 48 B apart, so a quarter-warp's LDS.128 hit 32 banks
 constexpr int PITCH3 = GRP3 * SLOT3 + 4;    // 220 floats (== 28 mod 32: patch rows on distinct banks)
-constexpr int SELF3 = kNlmPast * 17 + kNlmRangeFreq;   // candidate (dt 0, df 0): d == 0 exactly
 constexpr int WPITCH3 = 360;                // scratch floats per (target, block): 357 candidates
 constexpr int GATED3 = 357;                 // bit 357 of the field: block skipped by the energy gate
 constexpr int CHUNK3 = 2048;                // targets per launch pair (scratch stays in L2)
@@ -383,28 +382,29 @@ nlm3_paste_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int
   const unsigned fw[FW3] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
   float res = tv;
   if (!((fw[GATED3 >> 5] >> (GATED3 & 31)) & 1u)) {
-    float inv, thr;
-    block_params3(bs + 4, K, h, &inv, &thr);
-    const float w_self = schraudolph_exp3(-0.0f * inv);                   // d == 0
+    const float w_self = schraudolph_exp3(-0.0f);     // self candidate: d == 0 for every h_b
     const float* wp = Wg + (size_t)pair * WPITCH3;
     float acc = 0.f, ws = 0.f;
+    // dt-major walk: the 17 df bits of one dt are a bit field at a compile-time position, the
+    // pasted row pointer is hoisted, ascending bit = ascending df (the reference's order)
 #pragma unroll
-    for (int w = 0; w < FW3; w++) {
-      unsigned m = fw[w];
-      if (w == (GATED3 >> 5)) m &= (1u << (GATED3 & 31)) - 1u;
-      if (w == (SELF3 >> 5)) m |= 1u << (SELF3 & 31);  // the self candidate is always accepted
-      while (m) {                                      // ascending bit = (dt, df) order
+    for (int dti = 0; dti < NDT; dti++) {
+      constexpr int kDfBits = 2 * kNlmRangeFreq + 1;
+      const int p0 = dti * kDfBits, w0 = p0 >> 5, sh = p0 & 31;
+      unsigned m = fw[w0] >> sh;
+      if (sh + kDfBits > 32) m |= fw[w0 + 1 < FW3 ? w0 + 1 : w0] << (32 - sh);
+      m &= (1u << kDfBits) - 1u;
+      if (dti == kNlmPast) m |= 1u << kNlmRangeFreq;   // the self candidate is always accepted
+      const float* prow = trow + (ptrdiff_t)(dti - kNlmPast) * pitchS;   // frame t + dt
+      const float* wrow = wp + p0;
+      while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1;
-        const int cand = w * 32 + bit;
-        const int dti = cand / 17;
-        const int df = cand - dti * 17 - kNlmRangeFreq;
-        const float wgt = (cand == SELF3) ? w_self : wp[cand];
+        const float wgt = (dti == kNlmPast && bit == kNlmRangeFreq) ? w_self : wrow[bit];
         if (!(wgt < kNlmMinWeight)) {                  // nlm_filter_avx.c:219-221
-          int c = bs + j + df;                         // pasted frame t + dt, bin clamp(bs + j + df)
+          int c = bs + j + bit - kNlmRangeFreq;        // bin clamp(bs + j + df)
           c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
-          const float v = trow[(ptrdiff_t)(dti - kNlmPast) * pitchS + c];
-          acc = fmaf(wgt, v, acc);
+          acc = fmaf(wgt, prow[c], acc);
           ws += wgt;
         }
       }
