@@ -26,6 +26,7 @@ namespace sb {
 //        SPP:    psd, smoothed_spp
 //        Martin: psd, cur_min, hist[8]
 constexpr int kEstHeader = 32;
+constexpr int kBatch = 16;   // frames whose loads are in flight per thread in the scans
 
 namespace {
 
@@ -87,10 +88,22 @@ __global__ void spp_scan_kernel(const GeoK g, const float* __restrict__ P,
   float psd = a[k], sspp = a[g.Kp + k];
   bool first = est[0] != 0.f;
   const float fl = floorv[k];
-  for (int f = 0; f < frames; f++) {
+  // the loads do not depend on the recurrence: fetch kBatch frames, then run the chain
+  for (int f0 = 0; f0 < frames; f0 += kBatch) {
+    float pb[kBatch], eb[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; i++) {
+      const bool in = f0 + i < frames;
+      pb[i] = in ? P[(size_t)(f0 + i) * g.Kp + k] : 0.f;
+      eb[i] = in ? energy[f0 + i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; i++) {
+    const int f = f0 + i;
+    if (f >= frames) break;
     const size_t o = (size_t)f * g.Kp + k;
-    const float p = P[o];
-    const bool silent = energy[f] < kSilenceThreshold;
+    const float p = pb[i];
+    const bool silent = eb[i] < kSilenceThreshold;
     float res;
     if (first) {
       if (silent) {
@@ -111,6 +124,7 @@ __global__ void spp_scan_kernel(const GeoK g, const float* __restrict__ P,
     }
     out[o] = res;
     if (psd < fl) psd = fl;   // apply_floor, every frame (spp:182-194)
+    }
   }
   a[k] = psd;
   a[g.Kp + k] = sspp;
@@ -132,10 +146,21 @@ __global__ void martin_scan_kernel(const GeoK g, const float* __restrict__ P,
   unsigned fc = (unsigned)est[1];
   unsigned idx = (unsigned)est[2];
   const float fl = floorv[k];
-  for (int f = 0; f < frames; f++) {
+  for (int f0 = 0; f0 < frames; f0 += kBatch) {
+    float pb[kBatch], eb[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; i++) {
+      const bool in = f0 + i < frames;
+      pb[i] = in ? P[(size_t)(f0 + i) * g.Kp + k] : 0.f;
+      eb[i] = in ? energy[f0 + i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; i++) {
+    const int f = f0 + i;
+    if (f >= frames) break;
     const size_t o = (size_t)f * g.Kp + k;
-    const float p = P[o];
-    const bool silent = energy[f] < kSilenceThreshold;
+    const float p = pb[i];
+    const bool silent = eb[i] < kSilenceThreshold;
     float res;
     bool emitted = false;
     if (first) {
@@ -178,6 +203,7 @@ __global__ void martin_scan_kernel(const GeoK g, const float* __restrict__ P,
 #pragma unroll
     for (int d = 0; d < kMartinSubwinCount; d++)
       if (hist[d] < fl) hist[d] = fl;
+    }
   }
   a[k] = psd;
   a[g.Kp + k] = cmin;
