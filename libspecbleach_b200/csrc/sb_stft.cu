@@ -127,10 +127,14 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
     } else {
       // generic radix: one work item per output point; the r-term sum runs in
       // double with double roots of unity and is rounded to float once
+      // consecutive threads take consecutive butterflies of the SAME output index t, so a warp
+      // needs only a few distinct roots per term (the root loads were the bottleneck of the
+      // radix-167 pass of N = 3006 when every lane asked for a different one)
       const double2* __restrict__ root = g.twg + g.twg_off[f];
+      const int nbf = M / r;
       for (int item = threadIdx.x; item < M; item += blockDim.x) {
-        const int idx = item / r;        // butterfly
-        const int t = item - idx * r;    // output index inside the butterfly
+        const int t = item / nbf;        // output index inside the butterfly
+        const int idx = item - t * nbf;  // butterfly
         const int j = idx / s;
         const int q = idx - j * s;
         const float2 v0 = x[q + s * j];
