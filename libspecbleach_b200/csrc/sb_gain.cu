@@ -483,9 +483,9 @@ nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
 //           T = (T_f^p + (T_prev*fwd)^p + (T_fut*bwd)^p)^(1/p), masking_estimator.c:270-288;
 //           T = u^(1/0.6) is taken in nmr_kernel), A -> B
 // ---------------------------------------------------------------------------
-constexpr int kRsTile = 32;      // frames per tile
-constexpr int kRsRing = 8;       // tiles resident in shared memory
-constexpr int kRsAhead = 5;      // prefetch distance (tiles)
+constexpr int kRsTile = 64;      // frames per tile
+constexpr int kRsRing = 5;       // tiles resident in shared memory
+constexpr int kRsAhead = 3;      // prefetch distance (tiles)
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
