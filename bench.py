@@ -241,7 +241,21 @@ def run_ours(args):
     for p, c in zip(x_pin, chans):
         p.array[:] = c
 
-    def step(device: bool):
+    def step(device: bool, serial: bool = False):
+        if serial:
+            # one channel after the other: only one lane is busy, so the CUDA events around a
+            # launch time that launch alone (roofline pass)
+            for c in range(CHANNELS):
+                den[c].reset_profile()
+                den[c].load_parameters(learn_noise=1)
+                if not sb.process_batch([den[c]], [(x_dev[c].data_ptr(), n_learn)],
+                                        [(y_dev[c].data_ptr(), n_learn)], device=True):
+                    raise RuntimeError(sb.last_error())
+                den[c].load_parameters(**PARAMS)
+                if not sb.process_batch([den[c]], [(x_dev[c].data_ptr() + 4 * n_learn, n - n_learn)],
+                                        [(y_dev[c].data_ptr() + 4 * n_learn, n - n_learn)], device=True):
+                    raise RuntimeError(sb.last_error())
+            return
         for d in den:
             d.reset_profile()
             d.load_parameters(learn_noise=1)
@@ -272,7 +286,7 @@ def run_ours(args):
 
     def timed(device: bool, steps: int, warmup: int, profile: bool):
         for _ in range(warmup):
-            step(device)
+            step(device, serial=profile)
         barrier()
         L.specbleach_b200_profile(1 if profile else 0)
         L.specbleach_b200_stats_reset()
@@ -282,7 +296,7 @@ def run_ours(args):
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(device)
+            step(device, serial=profile)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -297,8 +311,8 @@ def run_ours(args):
 
     ms_dev, clocks, st_cnt = timed(True, args.steps, args.warmup, False)
     ms_e2e, clocks_e2e, st_e2e = timed(False, args.steps, max(1, args.warmup // 2), False)
-    # roofline pass: the same steps again with CUDA events around every launch on its lane
-    # stream (its wall time is NOT the reported value)
+    # roofline pass: the same steps again, one channel at a time, with CUDA events around every
+    # launch on its lane stream (its wall time is NOT the reported value)
     ms_prof, _, st_dev = timed(True, args.steps, 0, True)
     classes = api.class_stats()
 
