@@ -112,6 +112,28 @@ def test_cuda_matches_reference_build(gpu, ref, name, two_d, sr, ms, prm, chunk)
     assert_parity(got, want, name)
 
 
+GEOMETRIES = [(8000, 32.0), (22050, 46.0), (44100, 23.2), (48000, 5.0), (48000, 100.0), (88200, 50.0),
+              (192000, 20.0), (192000, 100.0), (96000, 170.0)]
+
+
+@pytest.mark.parametrize("sr,ms", GEOMETRIES, ids=[f"{a}Hz_{b}ms" for a, b in GEOMETRIES])
+def test_unusual_geometries_match_reference_build(gpu, ref, sr, ms):
+    """frame sizes from 240 to 19 200 samples, fft sizes with factors 2, 3, 5, 7, 11, 19, 107, 521
+    ... (fft_transform.c:44-63: N = frame + 800 rounded to even): latency, profile size and PCM
+    of both denoisers (tools: tests/gpu_geometry_sweep.py)."""
+    x = synth(2.5, sr, 7)
+    for two_d in (True, False):
+        r = ref.RefDenoiser(sr, ms, two_d)
+        d = gpu.Denoiser(sr, ms, two_d)
+        assert (r.latency(), r.profile_size()) == (d.latency(), d.profile_size())
+        prm = P2D if two_d else P1D
+        want = run_flow(r, x, sr, prm, 8192)
+        got = run_flow(d, x, sr, prm, 7001)
+        assert_parity(got, want, f"{sr} Hz / {ms} ms two_d={two_d}")
+        d.close()
+        r.close()
+
+
 ADAPTIVE = [("2d_spp", True, 0, 0), ("2d_martin", True, 2, 0), ("1d_spp", False, 0, 0),
             ("1d_martin", False, 2, 0), ("2d_spp_learned", True, 0, 44100),
             ("2d_brandt", True, 1, 0), ("1d_brandt", False, 1, 0), ("2d_brandt_learned", True, 1, 44100)]
