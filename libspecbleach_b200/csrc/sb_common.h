@@ -127,6 +127,16 @@ struct Lane {
   float* band_T = nullptr;     // [F][32]
   float* band_p = nullptr;     // [F][32]
   float* frame_flag = nullptr; // [F] frame energy (adaptive estimators)
+  // host I/O pipeline: H2D of sub-call k+1 and D2H of sub-call k-1 overlap the kernels of
+  // sub-call k (two staging buffers each way, dedicated copy streams, events)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  float* in_stage[2] = {nullptr, nullptr};   // [samples] incoming PCM
+  float* out_stage[2] = {nullptr, nullptr};  // [samples] outgoing PCM
+  cudaEvent_t ev_in[2] = {nullptr, nullptr};    // H2D into in_stage[b] finished
+  cudaEvent_t ev_used[2] = {nullptr, nullptr};  // in_stage[b] consumed by the compute stream
+  cudaEvent_t ev_out[2] = {nullptr, nullptr};   // out_stage[b] written by the compute stream
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};  // D2H from out_stage[b] finished
+  unsigned io_seq = 0;                          // host sub-calls enqueued on this lane
   std::vector<cudaEvent_t> ev; // profiling event pairs (NLM)
 };
 

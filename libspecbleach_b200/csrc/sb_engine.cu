@@ -84,7 +84,8 @@ static bool dev_zalloc(float** p, size_t floats) {
 static void lane_free(Lane& L) {
   float** bufs[] = {&L.xbuf, &L.ybuf, &L.Xre, &L.Xim, &L.P, &L.noise, &L.S, &L.Shat, &L.Mg,
                     &L.alpha, &L.stable, &L.wt, &L.mask, &L.Yre, &L.Yim, &L.synth,
-                    &L.band_a, &L.band_T, &L.band_p, &L.frame_flag};
+                    &L.band_a, &L.band_T, &L.band_p, &L.frame_flag, &L.in_stage[0],
+                    &L.in_stage[1], &L.out_stage[0], &L.out_stage[1]};
   for (float** b : bufs) {
     if (*b) cudaFree(*b);
     *b = nullptr;
@@ -98,14 +99,29 @@ static bool lane_ensure(Lane& L, const GeoK& g, int F) {
   // (what torch.cuda.Event uses) then brackets the work of every lane, while
   // lanes still overlap with each other.
   if (!L.stream) SB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamDefault));
+  if (!L.s_in) {
+    SB_CUDA(cudaStreamCreateWithFlags(&L.s_in, cudaStreamDefault));
+    SB_CUDA(cudaStreamCreateWithFlags(&L.s_out, cudaStreamDefault));
+    for (int b = 0; b < 2; b++) {
+      SB_CUDA(cudaEventCreateWithFlags(&L.ev_in[b], cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&L.ev_used[b], cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&L.ev_out[b], cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&L.ev_done[b], cudaEventDisableTiming));
+    }
+  }
   const size_t samples = (size_t)g.frame + (size_t)(F + 1) * g.hop;
   if (L.cap_frames >= F && L.cap_Kp >= g.Kp && L.cap_frame_p >= g.frame_p &&
       L.cap_samples >= samples)
     return true;
   SB_CUDA(cudaStreamSynchronize(L.stream));
+  SB_CUDA(cudaStreamSynchronize(L.s_in));
+  SB_CUDA(cudaStreamSynchronize(L.s_out));
   lane_free(L);
+  L.io_seq = 0;
   const size_t Kp = g.Kp, R = (size_t)F;
   bool ok = dev_alloc(&L.xbuf, samples) && dev_alloc(&L.ybuf, samples) &&
+            dev_alloc(&L.in_stage[0], samples) && dev_alloc(&L.in_stage[1], samples) &&
+            dev_alloc(&L.out_stage[0], samples) && dev_alloc(&L.out_stage[1], samples) &&
             dev_alloc(&L.Xre, (R + 4) * Kp) && dev_alloc(&L.Xim, (R + 4) * Kp) &&
             dev_alloc(&L.P, R * Kp) && dev_alloc(&L.noise, (R + 4) * Kp) &&
             dev_alloc(&L.S, (R + kSnrHist) * Kp) && dev_alloc(&L.Shat, R * Kp) &&
@@ -511,6 +527,8 @@ static bool is_device_or_pinned(const void* p) {
 bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, bool device_io) {
   SB_CUDA(cudaSetDevice(h->device));
   uint32_t pos = 0;
+  bool host_pending = false;
+  int last_b = 0;
   while (pos < n) {
     uint32_t m = n - pos;
     const uint32_t cap = max_sub_samples(h);
@@ -521,12 +539,34 @@ bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, b
       if (!d2d(dst, in + pos, m, L.stream)) return false;
       if (!sub_run(h, L, m, out + pos)) return false;
     } else {
-      SB_CUDA(cudaMemcpyAsync(dst, in + pos, m * sizeof(float), cudaMemcpyHostToDevice, L.stream));
-      if (!sub_run(h, L, m, L.ybuf)) return false;
-      SB_CUDA(cudaMemcpyAsync(out + pos, L.ybuf, m * sizeof(float), cudaMemcpyDeviceToHost,
-                              L.stream));
+      // H2D on its own stream into a staging buffer (it may run while the kernels of the
+      // previous sub-call are still busy), kernels on the lane stream, D2H on a third stream
+      const int b = (int)(L.io_seq & 1u);
+      const bool reused = L.io_seq >= 2;
+      L.io_seq++;
+      if (reused) SB_CUDA(cudaStreamWaitEvent(L.s_in, L.ev_used[b], 0));
+      SB_CUDA(cudaMemcpyAsync(L.in_stage[b], in + pos, m * sizeof(float), cudaMemcpyHostToDevice,
+                              L.s_in));
+      SB_CUDA(cudaEventRecord(L.ev_in[b], L.s_in));
+      SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_in[b], 0));
+      if (!d2d(dst, L.in_stage[b], m, L.stream)) return false;
+      SB_CUDA(cudaEventRecord(L.ev_used[b], L.stream));
+      if (reused) SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_done[b], 0));
+      if (!sub_run(h, L, m, L.out_stage[b])) return false;
+      SB_CUDA(cudaEventRecord(L.ev_out[b], L.stream));
+      SB_CUDA(cudaStreamWaitEvent(L.s_out, L.ev_out[b], 0));
+      SB_CUDA(cudaMemcpyAsync(out + pos, L.out_stage[b], m * sizeof(float), cudaMemcpyDeviceToHost,
+                              L.s_out));
+      SB_CUDA(cudaEventRecord(L.ev_done[b], L.s_out));
+      // whoever synchronises the lane stream also waits for this copy
+      host_pending = true;
+      last_b = b;
     }
     pos += m;
+  }
+  if (host_pending) {
+    // the D2H copies are ordered on s_out: waiting for the last one waits for all
+    SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_done[last_b], 0));
   }
   (void)is_device_or_pinned;
   return true;
