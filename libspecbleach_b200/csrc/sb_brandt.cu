@@ -12,7 +12,7 @@
 // Whole-call form: the sorted window of a frame depends only on the H most
 // recent non-silent frames, so frames are evaluated independently:
 //   1. compact the non-silent frames of the call (silence gate, :138-143,169-173)
-//   2. brandt_eval_kernel: one warp per (bin, tile of 32 consecutive non-silent
+//   2. brandt_eval_kernel: one warp per (bin, tile of 64 consecutive non-silent
 //      frames).  The tile's first window is rank-sorted from scratch; every next
 //      window is the previous one with the oldest value removed and the new one
 //      inserted (one scatter pass through shared memory).  The five fits are
@@ -34,7 +34,7 @@
 
 namespace sb {
 
-constexpr int kBrandtTile = 32;        // consecutive non-silent frames per warp
+constexpr int kBrandtTile = 64;        // consecutive non-silent frames per warp
 constexpr int kBrandtHdrIndex = 3;     // est[3] = history_index
 constexpr int kEstHeaderB = 32;        // same header size as sb_adaptive.cu
 
@@ -226,40 +226,66 @@ brandt_eval_kernel(const GeoK g, BrandtCfg c, const float* __restrict__ P,
     if (raw_old) need_sort = true;
 
     // ---- the five trimmed-exponential fits (:198-241, calculate_ad_norm :113-132) ----
+    // pass 1: trimmed sums.  (i0, ci) pairs with i0 >= q[ci] are skipped warp-uniformly
     float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = lane; i < H; i += 32) {
-      const float v = cur[i];
+    for (int i0 = 0; i0 < H; i0 += 32) {
+      const int i = i0 + lane;
+      const float v = i < H ? cur[i] : 0.f;
 #pragma unroll
       for (int ci = 0; ci < 5; ci++)
-        if (i < c.q[ci]) ps[ci] += v;
+        if (i0 < c.q[ci] && i < c.q[ci]) ps[ci] += v;
+    }
+    float tot1[5];
+#pragma unroll
+    for (int ci = 0; ci < 5; ci++) tot1[ci] = warp_sum(ps[ci]);
+    // per-fit scalars: lane ci computes fit ci (IEEE divisions, one expf), then broadcast
+    float s_mu = 0.f, s_mu_inv = 0.f, s_den_inv = 0.f, s_q_inv = 0.f;
+    int s_flags = 0;                                   // bit 0: ok, bit 1: live
+    {
+      float t = tot1[0];
+      int q = c.q[0];
+      float cf = c.cf[0];
+#pragma unroll
+      for (int ci = 1; ci < 5; ci++)
+        if (lane == ci) { t = tot1[ci]; q = c.q[ci]; cf = c.cf[ci]; }
+      const float mu_trunc = __fdiv_rn(t, (float)q);
+      const bool okc = q >= 10 && mu_trunc > kSilenceThreshold;
+      s_mu = __fmul_rn(mu_trunc, cf);
+      bool livec = okc && !(s_mu < 1e-15f);
+      s_mu_inv = __fdiv_rn(1.0f, s_mu);
+      s_q_inv = __fdiv_rn(1.0f, (float)q);
+      const float b = cur[q > 0 ? q - 1 : 0];
+      const float den = 1.0f - expf(-__fmul_rn(b, s_mu_inv));
+      if (fabsf(den) < kSpectralEps) livec = false;
+      s_den_inv = __fdiv_rn(1.0f, den);
+      s_flags = (okc ? 1 : 0) | (livec ? 2 : 0);
     }
     float mu[5], mu_inv[5], den_inv[5], q_inv[5];
     bool ok[5], live[5];
 #pragma unroll
     for (int ci = 0; ci < 5; ci++) {
-      const int q = c.q[ci];
-      const float tot = warp_sum(ps[ci]);
-      const float mu_trunc = __fdiv_rn(tot, (float)q);
-      ok[ci] = q >= 10 && mu_trunc > kSilenceThreshold;
-      mu[ci] = __fmul_rn(mu_trunc, c.cf[ci]);
-      live[ci] = ok[ci] && !(mu[ci] < 1e-15f);
-      mu_inv[ci] = __fdiv_rn(1.0f, mu[ci]);
-      q_inv[ci] = __fdiv_rn(1.0f, (float)q);
-      const float b = cur[q > 0 ? q - 1 : 0];
-      const float den = 1.0f - expf(-__fmul_rn(b, mu_inv[ci]));
-      if (fabsf(den) < kSpectralEps) live[ci] = false;
-      den_inv[ci] = __fdiv_rn(1.0f, den);
+      mu[ci] = __shfl_sync(0xffffffffu, s_mu, ci);
+      mu_inv[ci] = __shfl_sync(0xffffffffu, s_mu_inv, ci);
+      den_inv[ci] = __shfl_sync(0xffffffffu, s_den_inv, ci);
+      q_inv[ci] = __shfl_sync(0xffffffffu, s_q_inv, ci);
+      const int fl = __shfl_sync(0xffffffffu, s_flags, ci);
+      ok[ci] = (fl & 1) != 0;
+      live[ci] = (fl & 2) != 0;
     }
+    // pass 2: L1 distance between the empirical and the truncated-exponential CDF
     float ts[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = lane; i < H; i += 32) {
-      const float v = cur[i];
+    for (int i0 = 0; i0 < H; i0 += 32) {
+      const int i = i0 + lane;
+      const float v = i < H ? cur[i] : 0.f;
       const float fi = (float)(i + 1);
 #pragma unroll
       for (int ci = 0; ci < 5; ci++) {
-        if (i < c.q[ci] && live[ci]) {
-          const float e1 = 1.0f - expf(-__fmul_rn(v, mu_inv[ci]));
-          const float fe = __fmul_rn(fi, q_inv[ci]);
-          ts[ci] += fabsf(fmaf(-e1, den_inv[ci], fe));     // gcc emits one vfnmadd here
+        if (i0 < c.q[ci] && live[ci]) {                // warp-uniform
+          if (i < c.q[ci]) {
+            const float e1 = 1.0f - expf(-__fmul_rn(v, mu_inv[ci]));
+            const float fe = __fmul_rn(fi, q_inv[ci]);
+            ts[ci] += fabsf(fmaf(-e1, den_inv[ci], fe));   // gcc emits one vfnmadd here
+          }
         }
       }
     }
