@@ -139,6 +139,32 @@ def _ref_worker(seed, seconds, barrier, q):
     q.put(dt)
 
 
+def _ref_single_stream(seconds, q):
+    os.environ["OMP_NUM_THREADS"] = "4"      # the library's default NLM thread count
+    from oracle import ref_binding as rb
+    from libspecbleach_b200.synth import speech_plus_noise
+    x = speech_plus_noise(seconds, SR, 9001)
+    d = rb.RefDenoiser(SR, FRAME_MS, True)
+    t0 = time.perf_counter()
+    d.load_parameters(learn_noise=1)
+    d.process(x[:int(LEARN_SECONDS * SR)])
+    d.load_parameters(**PARAMS)
+    d.process(x[int(LEARN_SECONDS * SR):])
+    q.put(time.perf_counter() - t0)
+
+
+def cpu_reference_single_stream(sample_seconds: float):
+    """ONE mono stream with the library's default 4 NLM threads, x realtime (mono)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=_ref_single_stream, args=(sample_seconds, q))
+    p.start()
+    dt = q.get(timeout=600)
+    p.join()
+    return sample_seconds / dt
+
+
 def cpu_reference_throughput(sample_seconds: float, steps: int, warmup: int, workers: int | None = None):
     """x realtime (stereo) of the reference build with every host thread busy:
     `workers` independent mono streams in parallel processes, OMP_NUM_THREADS=1 each."""
@@ -211,6 +237,8 @@ def run_ours(args):
         try:
             r = cpu_reference_throughput(args.cpu_sample_seconds, 1, 0)
             cpu_pre = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build")}
+            cpu_pre["single_stream_4_omp_threads_x_realtime_mono"] = cpu_reference_single_stream(
+                args.cpu_sample_seconds)
         except Exception as e:  # noqa: BLE001
             cpu_pre = {"value": None, "unit": "x realtime", "cores": 0, "kind": "reference",
                        "sample": f"unavailable: {e!r}"}
