@@ -279,6 +279,7 @@ bool launch_nlm(const GeoK& g, const float* S, int first_target_row, int targets
 // sb_nlm3.cu (full paste blocks only; launch_nlm adds the tail kernel)
 bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int targets, float h,
                  float* Shat, cudaStream_t st);
+int nlm3_chunk_targets(int K);   // targets per NLM chunk: whole waves of CTAs on this device
 
 // sb_gain.cu
 struct GainArgs {

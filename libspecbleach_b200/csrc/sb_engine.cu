@@ -142,11 +142,19 @@ static bool lane_ensure(Lane& L, const GeoK& g, int F) {
   return true;
 }
 
+int sub_call_frames(const GeoK& g) {
+  const int c = ctx().chunk_frames;
+  if (c > 0) return c;
+  int f = 2 * nlm3_chunk_targets(g.K);       // default: two full NLM chunks per sub-call
+  if (f > 8192) f = nlm3_chunk_targets(g.K); // large spectra: one chunk
+  return f < 32 ? 32 : f;
+}
+
 Lane* get_lane(int idx, const GeoK& g) {
   Context& c = ctx();
   if ((int)c.lanes.size() < c.num_lanes) c.lanes.resize(c.num_lanes);
   Lane& L = c.lanes[idx % c.num_lanes];
-  if (!lane_ensure(L, g, c.chunk_frames)) return nullptr;
+  if (!lane_ensure(L, g, sub_call_frames(g))) return nullptr;
   return &L;
 }
 
@@ -507,7 +515,7 @@ void after_sync(Handle* h) {
 
 uint32_t max_sub_samples(const Handle* h) {
   const GeoK& g = h->geo->k;
-  return (uint32_t)ctx().chunk_frames * (uint32_t)g.hop - h->carry;
+  return (uint32_t)sub_call_frames(g) * (uint32_t)g.hop - h->carry;
 }
 
 // ---------------------------------------------------------------------------

@@ -6,7 +6,7 @@
 namespace sb {
 
 struct Context {
-  int chunk_frames = 4096;   // frames per internal sub-call
+  int chunk_frames = 0;      // frames per internal sub-call; 0 = two NLM chunks of the geometry
   int num_lanes = 4;
   std::vector<Lane> lanes;
   // instrumentation
@@ -18,6 +18,7 @@ struct Context {
   uint64_t class_launches[kcCount] = {0};
 };
 Context& ctx();
+int sub_call_frames(const GeoK& g);   // chunk_frames, or its per-geometry default
 
 void set_error_msg(const char* msg);
 

@@ -50,7 +50,7 @@ constexpr int SLOT3 = 12;                   // floats per column group: consecut
 constexpr int PITCH3 = GRP3 * SLOT3 + 4;    // 220 floats (== 28 mod 32: patch rows on distinct banks)
 constexpr int WPITCH3 = 360;                // scratch floats per (target, block): 357 candidates
 constexpr int GATED3 = 357;                 // bit 357 of the field: block skipped by the energy gate
-constexpr int CHUNK3 = 2048;                // targets per launch pair (scratch stays in L2)
+constexpr int CHUNK3 = 2048;                // nominal targets per launch pair (scratch stays in L2)
 constexpr int NW3 = 12;                     // warps
 constexpr int NTH3 = NW3 * 32;              // 384 threads
 constexpr int FW3 = 12;                     // flag words per (target, block): 21*17 = 357 bits
@@ -416,6 +416,26 @@ nlm3_paste_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int
 
 }  // namespace
 
+// Targets per chunk: close to CHUNK3, and such that the grid of the distance kernel (target tiles
+// x block tiles, one CTA per SM) fills whole waves of the device's SMs.
+int nlm3_chunk_targets(int K) {
+  const int nfull = K / 8;
+  const int btiles = (nfull + NB3 - 1) / NB3;
+  if (btiles <= 0) return CHUNK3;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  int waves = (CHUNK3 / TT3 * btiles + sms / 2) / sms;      // nearest whole number of waves
+  if (waves < 1) waves = 1;
+  int ttiles = waves * sms / btiles;
+  if (ttiles < 1) ttiles = 1;
+  return ttiles * TT3;
+}
+
 // Scratch per stream (= per engine lane): weights and bit fields of one chunk of targets.
 struct Scratch3 {
   float* W = nullptr;
@@ -435,11 +455,12 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM3));
     attr_set = true;
   }
+  const int chunk = nlm3_chunk_targets(g.K);
   Scratch3 sc;
   {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     Scratch3& ref = g_scratch[st];
-    const size_t need = (size_t)CHUNK3 * (size_t)nfull;
+    const size_t need = (size_t)chunk * (size_t)nfull;
     if (ref.pairs < need) {
       SB_CUDA(cudaStreamSynchronize(st));
       if (ref.W) cudaFree(ref.W);
@@ -453,8 +474,8 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   }
   // rows of S that exist: the last target's +4 look-ahead row
   const int last_row = first_target_row + targets - 1 + kNlmFuture;
-  for (int t0 = 0; t0 < targets; t0 += CHUNK3) {
-    const int cnt = targets - t0 < CHUNK3 ? targets - t0 : CHUNK3;
+  for (int t0 = 0; t0 < targets; t0 += chunk) {
+    const int cnt = targets - t0 < chunk ? targets - t0 : chunk;
     dim3 grid((cnt + TT3 - 1) / TT3, (nfull + NB3 - 1) / NB3);
     nlm3_kernel<<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
                                            last_row, h, sc.W, sc.F);
