@@ -365,7 +365,10 @@ def run_ours(args):
         tf = ROOT / "profiles" / "nlm_traffic.json"
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+                per_target = json.loads(tf.read_text()).get("dram_bytes_per_target_frame")
+                blocks_per_frame = (1601 + 7) // 8
+                targets_per_launch = st_dev["nlm_frame_blocks"] / max(1, st_dev["nlm_launches"]) / blocks_per_frame
+                traffic = per_target * targets_per_launch
             except Exception:
                 traffic = None
         roofline = {
