@@ -71,6 +71,13 @@ void ktimer_end(int cls, cudaStream_t st) {
 static Context g_ctx;
 Context& ctx() { return g_ctx; }
 
+// The lanes (streams + scratch spectrograms) and the geometry cache are shared by all handles of
+// the process.  Distinct handles may be driven from different host threads (handles
+// are independent, the reference has no globals); every entry point that touches the device
+// takes this lock, so concurrent callers are serialised instead of racing on a lane.
+static std::recursive_mutex g_engine_mu;
+std::recursive_mutex& engine_mutex() { return g_engine_mu; }
+
 static bool dev_alloc(float** p, size_t floats) {
   SB_CUDA(cudaMalloc((void**)p, floats * sizeof(float)));
   return true;
@@ -162,6 +169,7 @@ Lane* get_lane(int idx, const GeoK& g) {
 // Handle lifecycle
 // ---------------------------------------------------------------------------
 Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error_msg("specbleach-b200: no CUDA device available (this build has no CPU fallback)");
@@ -197,6 +205,7 @@ Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms) {
 }
 
 void handle_destroy(Handle* h) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   if (!h) return;
   cudaDeviceSynchronize();
   float* bufs[] = {h->d_prof, h->d_med_ring, h->d_hist, h->d_tail[0], h->d_tail[1],
@@ -217,6 +226,7 @@ static void refresh_profile_learned(Handle* h) {
 }
 
 bool handle_load_parameters(Handle* h, const Params& p) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   // load_2d_reduction_parameters / load_reduction_parameters
   // (spectral_2d_denoiser.c:287-322, spectral_denoiser.c:236-256)
   if (p.adaptive) {
@@ -581,6 +591,7 @@ bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, b
 }
 
 bool process_call(Handle* h, uint32_t n, const float* in, float* out, bool device_io) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   if (!h->params_loaded) {
     // the reference processes with zero-initialised parameters; we do the same
     Params p;          // calloc'd Denoiser2DParameters: every field zero
@@ -602,6 +613,7 @@ bool process_call(Handle* h, uint32_t n, const float* in, float* out, bool devic
 
 bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* const* in,
                    float* const* out, bool device_io) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   if (count == 0) return true;
   Context& c = ctx();
   bool ok = true;

@@ -3,6 +3,8 @@
 
 #include "sb_common.h"
 
+#include <mutex>
+
 namespace sb {
 
 struct Context {
@@ -18,6 +20,7 @@ struct Context {
   uint64_t class_launches[kcCount] = {0};
 };
 Context& ctx();
+std::recursive_mutex& engine_mutex();   // serialises device work of concurrent host threads
 int sub_call_frames(const GeoK& g);   // chunk_frames, or its per-geometry default
 
 void set_error_msg(const char* msg);

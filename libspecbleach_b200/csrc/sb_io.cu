@@ -162,6 +162,7 @@ size_t state_size(Handle* h) {
 }
 
 bool state_save(Handle* h, void* blob, size_t bytes) {
+  std::lock_guard<std::recursive_mutex> engine_lock(engine_mutex());
   if (bytes < state_size(h)) {
     set_error_msg("specbleach-b200: state buffer too small (see specbleach_b200_state_size)");
     return false;
@@ -216,6 +217,7 @@ bool state_save(Handle* h, void* blob, size_t bytes) {
 }
 
 bool state_load(Handle* h, const void* blob, size_t bytes) {
+  std::lock_guard<std::recursive_mutex> engine_lock(engine_mutex());
   const unsigned char* p = static_cast<const unsigned char*>(blob);
   StateHeader hd;
   if (bytes < sizeof(hd) + sizeof(StateScalars) + 4) {
@@ -357,6 +359,7 @@ interleave_kernel(const float* __restrict__ planar, size_t plane_pitch, int form
 
 bool process_interleaved(Handle** hs, uint32_t channels, uint32_t frames, int format,
                          const void* in, void* out) {
+  std::lock_guard<std::recursive_mutex> engine_lock(engine_mutex());
   if (!hs || channels == 0 || frames == 0 || !in || !out || format < 0 || format > 3) return false;
   for (uint32_t c = 0; c < channels; c++)
     if (!hs[c]) return false;

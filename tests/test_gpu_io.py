@@ -177,3 +177,31 @@ def test_time_tiled_stream_equals_monolithic(gpu, two_d, prm):
     assert sorted(list(p0) + list(p1)) == sorted(pieces)
     both = stitch({**p0, **p1}, len(x))
     assert np.array_equal(both, tiled)
+
+
+def test_distinct_handles_from_concurrent_host_threads(gpu):
+    """SURVEY 8b threading contract: distinct handles are independent and may be driven from
+    different host threads (ctypes releases the GIL, so these calls really overlap on the
+    host); each thread's output equals the single-threaded result."""
+    import threading
+    sr = 48000
+    xs = [synth(4.0, sr, 70 + i) for i in range(4)]
+    want = [run_flow(gpu.Denoiser(sr, 50.0, i % 2 == 0), x, sr, P2D if i % 2 == 0 else P1D, 9000)
+            for i, x in enumerate(xs)]
+    got = [None] * 4
+    errs = []
+
+    def work(i):
+        try:
+            got[i] = run_flow(gpu.Denoiser(sr, 50.0, i % 2 == 0), xs[i], sr, P2D if i % 2 == 0 else P1D, 9000)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
