@@ -285,68 +285,6 @@ __global__ void gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------
-// per-bin scans over frames: (1D) release smoothing, then the stabilised
-// clean-signal EMA of the veto (masking_veto.c:137-147)
-// ---------------------------------------------------------------------------
-constexpr int kScanBatch = 16;   // independent loads kept in flight per thread
-
-__global__ void bin_scan_kernel(const GeoK g, int first_active, int active, int two_d,
-                                float smoothing, const float* __restrict__ P,
-                                const float* __restrict__ noise_t, float* __restrict__ Mg,
-                                float* __restrict__ stable, float* __restrict__ st_state,
-                                float* __restrict__ sp_state) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= g.K) return;
-  const size_t Kp = g.Kp;
-  float st = st_state[k];
-  size_t o = (size_t)first_active * Kp + k;
-  if (two_d) {
-    // the loads do not depend on the recurrence: fetch a batch, then chain the FMAs
-    for (int f = 0; f < active; f += kScanBatch) {
-      float c[kScanBatch];
-#pragma unroll
-      for (int i = 0; i < kScanBatch; i++)
-        c[i] = (f + i < active) ? stable[o + (size_t)i * Kp] : 0.f;
-#pragma unroll
-      for (int i = 0; i < kScanBatch; i++) {
-        if (f + i < active) {
-          st = (kVetoSmoothing * c[i]) + ((1.0f - kVetoSmoothing) * st);
-          stable[o + (size_t)i * Kp] = st;
-        }
-      }
-      o += (size_t)kScanBatch * Kp;
-    }
-  } else {
-    float sp = sp_state[k];
-    for (int f = 0; f < active; f += kScanBatch) {
-      float c[kScanBatch], n[kScanBatch];
-#pragma unroll
-      for (int i = 0; i < kScanBatch; i++) {
-        const bool in = f + i < active;
-        c[i] = in ? P[o + (size_t)i * Kp] : 0.f;
-        n[i] = in ? noise_t[o + (size_t)i * Kp] : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < kScanBatch; i++) {
-        if (f + i < active) {
-          // spectral_smoother.c:183-192 (release-only smoothing), state update :132-133
-          float v = c[i];
-          if (c[i] > sp) v = (smoothing * sp) + ((1.0f - smoothing) * c[i]);
-          sp = v;
-          Mg[o + (size_t)i * Kp] = v;
-          const float cl = fmaxf(v - n[i], 0.0f);
-          st = (kVetoSmoothing * cl) + ((1.0f - kVetoSmoothing) * st);
-          stable[o + (size_t)i * Kp] = st;
-        }
-      }
-      o += (size_t)kScanBatch * Kp;
-    }
-    sp_state[k] = sp;
-  }
-  st_state[k] = st;
-}
-
-// ---------------------------------------------------------------------------
 // (frame, band): band energies, spreading, tonality -> a_t[b]
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -563,6 +501,80 @@ rowscan_kernel(int ncols, int pitch, int rows, const float* A, float* B,   // B 
   if (warp == 0 && cv) state[col] = m;
 }
 
+// 1D variant of the staged scan: two coupled recurrences per bin over (P, noise) rows --
+// release-only smoothing of the power spectrum (spectral_smoother.c:183-192, state update
+// :132-133) and the stabilised clean-signal EMA of the veto (masking_veto.c:137-147).
+// P tiles become Mg tiles and noise tiles become `stable` tiles in place in shared memory.
+constexpr int kRs1Tile = 32, kRs1Ring = 5, kRs1Ahead = 3;
+
+__global__ void __launch_bounds__(256)
+rowscan1d_kernel(int ncols, int pitch, int rows, float smoothing, const float* P,
+                 const float* noise, float* Mg, float* stable, float* st_state, float* sp_state) {
+  __shared__ float ringP[kRs1Ring][kRs1Tile][32];
+  __shared__ float ringN[kRs1Ring][kRs1Tile][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 32 + lane;
+  const bool cv = col < ncols;
+  const int ntiles = (rows + kRs1Tile - 1) / kRs1Tile;
+  constexpr int kMovers = 7;
+  auto load_tile = [&](int t) {
+    if (warp > 0 && t < ntiles) {
+      for (int r = warp - 1; r < kRs1Tile; r += kMovers) {
+        const int f = t * kRs1Tile + r;
+        if (f < rows && cv) {
+          cp_async4(&ringP[t % kRs1Ring][r][lane], P + (size_t)f * pitch + col);
+          cp_async4(&ringN[t % kRs1Ring][r][lane], noise + (size_t)f * pitch + col);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  auto store_tile = [&](int tb) {
+    for (int r = warp - 1; r < kRs1Tile; r += kMovers) {
+      const int f = tb * kRs1Tile + r;
+      if (f < rows && cv) {
+        Mg[(size_t)f * pitch + col] = ringP[tb % kRs1Ring][r][lane];
+        stable[(size_t)f * pitch + col] = ringN[tb % kRs1Ring][r][lane];
+      }
+    }
+  };
+  float st = 0.f, sp = 0.f;
+  if (warp == 0 && cv) {
+    st = st_state[col];
+    sp = sp_state[col];
+  }
+  for (int t = 0; t < kRs1Ahead; t++) load_tile(t);
+  for (int t = 0; t < ntiles; t++) {
+    cp_async_wait<kRs1Ahead - 1>();
+    __syncthreads();
+    if (warp == 0) {
+      const int nr = (rows - t * kRs1Tile < kRs1Tile) ? rows - t * kRs1Tile : kRs1Tile;
+      float* pp = &ringP[t % kRs1Ring][0][lane];
+      float* pn = &ringN[t % kRs1Ring][0][lane];
+#pragma unroll 8
+      for (int r = 0; r < nr; r++) {
+        const float c = pp[r * 32], n = pn[r * 32];
+        float v = c;
+        if (c > sp) v = (smoothing * sp) + ((1.0f - smoothing) * c);
+        sp = v;
+        const float cl = fmaxf(v - n, 0.0f);
+        st = (kVetoSmoothing * cl) + ((1.0f - kVetoSmoothing) * st);
+        pp[r * 32] = v;
+        pn[r * 32] = st;
+      }
+    } else if (t > 0) {
+      store_tile(t - 1);
+    }
+    load_tile(t + kRs1Ahead);
+  }
+  __syncthreads();
+  if (warp > 0 && ntiles > 0) store_tile(ntiles - 1);
+  if (warp == 0 && cv) {
+    st_state[col] = st;
+    sp_state[col] = sp;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // (frame, bin): veto interpolation, Wiener gain, whitened floor, apply
 // ---------------------------------------------------------------------------
@@ -755,9 +767,10 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
         rowscan_kernel<0><<<(g.K + 31) / 32, 256, 0, st>>>(g.K, g.Kp, active, sp, sp, RsCoef(),
                                                            h.d_stable);
       } else {
-        bin_scan_kernel<<<(g.K + 127) / 128, 128, 0, st>>>(g, fa, active, 0, a.smoothing, L.P,
-                                                           L.noise, L.Mg, L.stable, h.d_stable,
-                                                           h.d_sp_prev);
+        const size_t o = (size_t)fa * g.Kp;
+        rowscan1d_kernel<<<(g.K + 31) / 32, 256, 0, st>>>(g.K, g.Kp, active, a.smoothing, L.P + o,
+                                                          L.noise + o, L.Mg + o, L.stable + o,
+                                                          h.d_stable, h.d_sp_prev);
       }
       SB_LAUNCH_CHECK();
       }
