@@ -132,7 +132,7 @@ __device__ __forceinline__ void rowterms3(const Lane3& L, int ra, int rp, float 
 // Rare path of pass 1: at least one of the lane's candidates passed.  Every one sets its bit in
 // the (target, block) field and leaves its weight at W[target][block][candidate].  cmask
 // drops c = 8 of the lower df half, which duplicates df = 0.
-__device__ __noinline__ void emit_slow3(unsigned* fl, float* w, int p0, unsigned cmask, float thr,
+__device__ __forceinline__ void emit_slow3(unsigned* fl, float* w, int p0, unsigned cmask, float thr,
                                         float inv, float d0, float d1, float d2, float d3,
                                         float d4, float d5, float d6, float d7, float d8) {
   const float d[NC3] = {d0, d1, d2, d3, d4, d5, d6, d7, d8};
