@@ -153,32 +153,43 @@ __device__ __forceinline__ void emit_slow3(unsigned* fl, float* w, int p0, unsig
 }
 
 // candidates that pass the hard threshold -> bit field + weights of (target tau, this paste block)
-__device__ __forceinline__ void emit_flags3(const Lane3& L, int tau, int dti, float (&d)[NC3],
-                                            bool edge) {
-  if (edge) {   // block-uniform: first / last block tile
-    // candidates whose centre clamps to bin 0 / K-1 have the patch of the candidate that
-    // sits on the edge (clamp_index is applied to the centre first)
-    if (L.lo_clamp) {
-#pragma unroll
-      for (int c = 0; c < 4; c++) d[c] = d[4];
-    }
-    if (L.g == 1 && L.hi_df < 8) {
-      float dh = d[3];
-#pragma unroll
-      for (int c = 4; c < 8; c++) dh = (L.hi_df == c) ? d[c] : dh;
-#pragma unroll
-      for (int c = 4; c < NC3; c++) d[c] = (c > L.hi_df) ? dh : d[c];
-    }
-  }
-  // the self candidate (dt 0, df 0: d == 0, always accepted) is pasted unconditionally by
-  // pass 2 and never flagged here, so that quiet tiles never take the slow path
-  if (dti == kNlmPast && L.g == 1) d[0] = 3.0e38f;
-  const float dmin = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])),
+//
+// Hot path: one min over the lane's 9 distances and one compare.  Everything that rewrites a
+// distance lives in the rare branch, so the row walk keeps its registers untouched:
+//  * candidates whose centre clamps to bin 0 / K-1 take the distance of the candidate that sits
+//    on the edge (clamp_index is applied to the centre first).  Their fixed-up distances are
+//    copies of other distances of the same lane, so min(original) <= min(fixed-up) and the
+//    un-fixed min is a conservative test;
+//  * the self candidate (dt 0, df 0: d == 0, always accepted) is pasted unconditionally by
+//    pass 2 and never flagged here, so that quiet tiles never take the rare branch.
+__device__ __forceinline__ void emit_flags3(const Lane3& L, int tau, int dti, const float (&d)[NC3],
+                                            bool edge, bool valid) {
+  const bool self = (dti == kNlmPast) && (L.g == 1);
+  const float d0 = self ? 3.0e38f : d[0];
+  const float dmin = fminf(fminf(fminf(d0, d[1]), fminf(d[2], d[3])),
                            fminf(fminf(d[4], d[5]), fminf(fminf(d[6], d[7]), d[8])));
-  if (!(dmin > L.thr) && ((L.live >> tau) & 1ull))
+  if (valid && !(dmin > L.thr) && ((L.live >> (tau & 63)) & 1ull)) {
+    float e[NC3];
+#pragma unroll
+    for (int c = 0; c < NC3; c++) e[c] = d[c];
+    if (edge) {   // block-uniform: first / last block tile
+      if (L.lo_clamp) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) e[c] = d[4];
+      }
+      if (L.g == 1 && L.hi_df < 8) {
+        float dh = d[3];
+#pragma unroll
+        for (int c = 4; c < 8; c++) dh = (L.hi_df == c) ? d[c] : dh;
+#pragma unroll
+        for (int c = 4; c < NC3; c++) e[c] = (c > L.hi_df) ? dh : d[c];
+      }
+    }
+    const unsigned cmask = (L.g == 0 ? 0xffu : 0x1ffu) & (self ? ~1u : ~0u);
     emit_slow3(L.flags + (size_t)tau * (NB3 * FW3), L.wout + (size_t)tau * L.wstride,
-               dti * 17 + 8 * L.g, L.g == 0 ? 0xffu : 0x1ffu, L.thr, L.inv, d[0], d[1], d[2], d[3],
-               d[4], d[5], d[6], d[7], d[8]);
+               dti * 17 + 8 * L.g, cmask, L.thr, L.inv, e[0], e[1], e[2], e[3], e[4], e[5], e[6],
+               e[7], e[8]);
+  }
 }
 
 // ---- a dt that never wraps: delay-tree accumulation ----
@@ -192,28 +203,29 @@ __device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int ta, int
     A[0][c] = A[1][c] = 0.f;
     B[0][c] = B[1][c] = B[2][c] = B[3][c] = 0.f;
   }
+  // rows ta .. tb+6, padded to a multiple of 4 steps (the padding rows are clamped into the
+  // tile and their distances never emitted), so that the unrolled body has no step guard
   const int steps = tb + 7;
   for (int i0 = ta; i0 < steps; i0 += 4) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int i = i0 + u;
-      if (i < steps) {                               // warp-uniform
-        const int ra = 12 + i;                       // tile row of frame t0 - 4 + i
-        float R0[NC3];
-        rowterms3(L, ra, ra + dt, R0);
-        float d[NC3];
+      int ra = 12 + i;                             // tile row of frame t0 - 4 + i
+      ra = ra > ROWS3 - 1 ? ROWS3 - 1 : ra;
+      float R0[NC3];
+      rowterms3(L, ra, ra + dt, R0);
+      float d[NC3];
 #pragma unroll
-        for (int c = 0; c < NC3; c++) {
-          const float a0 = R1[c] + R0[c];
-          const float b0 = A[u & 1][c] + a0;
-          d[c] = B[u & 3][c] + b0;
-          R1[c] = R0[c];
-          A[u & 1][c] = a0;
-          B[u & 3][c] = b0;
-        }
-        const int tau = i - 7;
-        if (tau >= ta) emit_flags3(L, tau, dti, d, edge);
+      for (int c = 0; c < NC3; c++) {
+        const float a0 = R1[c] + R0[c];
+        const float b0 = A[u & 1][c] + a0;
+        d[c] = B[u & 3][c] + b0;
+        R1[c] = R0[c];
+        A[u & 1][c] = a0;
+        B[u & 3][c] = b0;
       }
+      const int tau = i - 7;
+      emit_flags3(L, tau, dti, d, edge, tau >= ta && tau < tb);
     }
   }
 }
@@ -252,7 +264,7 @@ __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int ta, int 
       float d[NC3];
 #pragma unroll
       for (int c = 0; c < NC3; c++) d[c] = age[7][c];
-      emit_flags3(L, tau, dti, d, edge);
+      emit_flags3(L, tau, dti, d, edge, true);
     }
   }
 }
