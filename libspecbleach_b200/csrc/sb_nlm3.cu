@@ -377,11 +377,11 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
 }
 
 // Pass 2: 8 lanes per (target, block); lane j owns bin 8*b + j.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 nlm3_paste_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
                   int targets, float h, const float* __restrict__ Wg,
                   const unsigned* __restrict__ Fg, float* __restrict__ out, int pitchO) {
-  const int pair = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int pair = blockIdx.x * 16 + (threadIdx.x >> 3);
   const int j = threadIdx.x & 7;
   if (pair >= targets * nfull) return;
   const int tau = pair / nfull;
@@ -493,7 +493,7 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
                                            last_row, h, sc.W, sc.F);
     SB_LAUNCH_CHECK();
     const int pairs = cnt * nfull;
-    nlm3_paste_kernel<<<(pairs + 31) / 32, 256, 0, st>>>(S, g.Kp, g.K, nfull,
+    nlm3_paste_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
                                                          first_target_row + t0, cnt, h, sc.W, sc.F,
                                                          Shat + (size_t)t0 * g.Kp, g.Kp);
     SB_LAUNCH_CHECK();
