@@ -58,6 +58,7 @@ constexpr int kOverlap = 4;                     // :182 / :204
 constexpr int kZeroPad = 800;                   // :188 / :210
 constexpr int kMaxBands = 25;                   // critical_bands.c:25-28
 constexpr int kBandPitch = 32;                  // pitch of per-band arrays
+constexpr int kMaxBandTasks = 96;               // band-sum work units per frame
 
 constexpr int kDelayFrames = kNlmFuture;        // 2D look-ahead (nlm_filter.c:447-452)
 constexpr int kSnrHist = kNlmRing - 1;          // 20 SNR frames carried between calls
@@ -72,6 +73,13 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   int fac[14];
   int nb;                                // number of Bark bands (<= 25)
   int band_start[kMaxBands + 1];         // band b = [band_start[b], band_start[b+1])
+  // Bark bands differ wildly in width (3 bins ... two thirds of the spectrum): per-frame band
+  // sums are cut into tasks of <= task_bins bins, dealt round-robin to warps and added per band
+  // in task order (fixed order: deterministic)
+  int ntask;
+  short task_band[kMaxBandTasks];
+  int task_k[kMaxBandTasks + 1];         // task t covers bins [task_k[t], min(task_k[t]+task_bins, band end))
+  short band_task0[kMaxBands + 1];       // first task of band b
   float centre[kMaxBands];               // masking_veto.c:103-110
   float fwd_pow[kMaxBands];              // forward_decay[b]^0.6 (masking_estimator.c:148-157)
   float bwd;                             // backward_decay (masking_estimator.c:160)

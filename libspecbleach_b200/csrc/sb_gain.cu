@@ -309,12 +309,18 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
             float* __restrict__ band_a) {
   __shared__ float E[2][kBandPitch], SL[2][kBandPitch], SV[2][kBandPitch];
   __shared__ float LV[2][kBandPitch], SPR[2][kBandPitch];
+  __shared__ float PART[6][kMaxBandTasks];
+  __shared__ float TERM[2][kMaxBands][kMaxBands + 1];
   const int i = first_active + blockIdx.x;
   const size_t ro = (size_t)i * g.Kp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int b = warp; b < g.nb; b += nw) {
+  for (int task = warp; task < g.ntask; task += nw) {
+    const int b = g.task_band[task];
+    const int k0 = g.task_k[task];
+    const int kend = g.task_band[task + 1 < g.ntask ? task + 1 : task] == b && task + 1 < g.ntask
+                         ? g.task_k[task + 1] : g.band_start[b + 1];
     float e0 = 0.f, l0 = 0.f, v0 = 0.f, e1 = 0.f, l1 = 0.f, v1 = 0.f;
-    for (int k = g.band_start[b] + lane; k < g.band_start[b + 1]; k += 32) {
+    for (int k = k0 + lane; k < kend; k += 32) {
       const float s = stable[ro + k];
       const float sv = fmaxf(s, kSpectralEps);
       e0 += s; v0 += sv; l0 += log10f(sv);
@@ -327,9 +333,19 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
     e0 = warp_sum(e0); l0 = warp_sum(l0); v0 = warp_sum(v0);
     if (two_d) { e1 = warp_sum(e1); l1 = warp_sum(l1); v1 = warp_sum(v1); }
     if (lane == 0) {
-      E[0][b] = e0; SL[0][b] = l0; SV[0][b] = v0;
-      E[1][b] = e1; SL[1][b] = l1; SV[1][b] = v1;
+      PART[0][task] = e0; PART[1][task] = l0; PART[2][task] = v0;
+      PART[3][task] = e1; PART[4][task] = l1; PART[5][task] = v1;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < g.nb) {
+    const int b = threadIdx.x;
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = g.band_task0[b]; t < g.band_task0[b + 1]; t++)
+#pragma unroll
+      for (int q = 0; q < 6; q++) a[q] += PART[q][t];
+    E[0][b] = a[0]; SL[0][b] = a[1]; SV[0][b] = a[2];
+    E[1][b] = a[3]; SL[1][b] = a[4]; SV[1][b] = a[5];
   }
   __syncthreads();
   const int nspec = two_d ? 2 : 1;
@@ -338,15 +354,21 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
     if (b < g.nb) LV[s][b] = (10.0f * log10f(E[s][b] + kSpectralEps)) + kDbFsToSpl;
   }
   __syncthreads();
+  // spreading terms (E_j g(i-j, L_j))^0.4 for every (spectrum, band i, band j): all threads
+  for (int item = threadIdx.x; item < nspec * g.nb * g.nb; item += blockDim.x) {
+    const int s = item / (g.nb * g.nb);
+    const int r = item - s * (g.nb * g.nb);
+    const int b = r / g.nb, j = r - b * g.nb;
+    const float dz = (float)b - (float)j;
+    const float gain = spreading_gain(dz, LV[s][j]);
+    TERM[s][b][j] = powf(E[s][j] * gain, kAdditivityExp);
+  }
+  __syncthreads();
   if (threadIdx.x < nspec * kBandPitch) {
     const int s = threadIdx.x / kBandPitch, b = threadIdx.x % kBandPitch;
     if (b < g.nb) {
       float acc = 0.f;
-      for (int j = 0; j < g.nb; j++) {
-        const float dz = (float)b - (float)j;
-        const float gain = spreading_gain(dz, LV[s][j]);
-        acc += powf(E[s][j] * gain, kAdditivityExp);
-      }
+      for (int j = 0; j < g.nb; j++) acc += TERM[s][b][j];   // reference order (j ascending)
       const float spr = powf(acc, kInvAdd);
       // tonality (masking_estimator.c:320-349)
       const float bins = (float)g.band_start[b + 1] - (float)g.band_start[b];
@@ -378,29 +400,53 @@ nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
   const int i = first_active + blockIdx.x;
   const size_t ro = (size_t)i * g.Kp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int b = warp; b < g.nb; b += nw) {
+  __shared__ float SPLs[kBandPitch], VT[kBandPitch];
+  __shared__ float PN[2][kMaxBandTasks];
+  if (threadIdx.x < g.nb) {
+    const int b = threadIdx.x;
     const float T = powf(band_T[(size_t)i * kBandPitch + b], kInvPower);   // band_T holds u = T^0.6
     // absolute_hearing_thresholds.c:141-159
     const float spl = (10.0f * log10f(T + kSpectralEps)) + g.spl_ref;
     float vT = powf(10.0f, (spl - g.spl_ref) / 10.0f) - kSpectralEps;
     if (vT < 0.0f) vT = 0.0f;
+    SPLs[b] = spl;
+    VT[b] = vT;
+  }
+  __syncthreads();
+  for (int task = warp; task < g.ntask; task += nw) {
+    const int b = g.task_band[task];
+    const int k0 = g.task_k[task];
+    const int kend = g.task_band[task + 1 < g.ntask ? task + 1 : task] == b && task + 1 < g.ntask
+                         ? g.task_k[task + 1] : g.band_start[b + 1];
+    const float spl = SPLs[b], vT = VT[b];
     float sn = 0.f, sth = 0.f;
-    for (int k = g.band_start[b] + lane; k < g.band_start[b + 1]; k += 32) {
+    for (int k = k0 + lane; k < kend; k += 32) {
       sn += noise_t[ro + k];
       sth += (spl >= __ldg(&g.abs_thr_spl[k])) ? vT : __ldg(&g.abs_thr_lin[k]);
     }
     sn = warp_sum(sn);
     sth = warp_sum(sth);
     if (lane == 0) {
-      float p = 0.f;
-      if (g.band_start[b + 1] > g.band_start[b]) {   // masking_veto.c:178-213
-        const float nmr = 10.0f * log10f((sn + kSpectralEps) / (sth + kSpectralEps));
-        if (nmr <= 0.0f) p = 1.0f;
-        else if (nmr >= kVetoNmrRange) p = 0.0f;
-        else p = 1.0f - (nmr / kVetoNmrRange);
-      }
-      band_p[(size_t)i * kBandPitch + b] = p;
+      PN[0][task] = sn;
+      PN[1][task] = sth;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < g.nb) {
+    const int b = threadIdx.x;
+    float sn = 0.f, sth = 0.f;
+    for (int t = g.band_task0[b]; t < g.band_task0[b + 1]; t++) {
+      sn += PN[0][t];
+      sth += PN[1][t];
+    }
+    float p = 0.f;
+    if (g.band_start[b + 1] > g.band_start[b]) {   // masking_veto.c:178-213
+      const float nmr = 10.0f * log10f((sn + kSpectralEps) / (sth + kSpectralEps));
+      if (nmr <= 0.0f) p = 1.0f;
+      else if (nmr >= kVetoNmrRange) p = 0.0f;
+      else p = 1.0f - (nmr / kVetoNmrRange);
+    }
+    band_p[(size_t)i * kBandPitch + b] = p;
   }
 }
 

@@ -174,6 +174,33 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
       g.centre[b] = (float)start + ((float)(end - start) / 2.0f);   // masking_veto.c:103-110
     }
   }
+  // band-sum tasks: slices of at most task_bins bins, bands in order
+  {
+    int task_bins = 128;
+    for (;;) {
+      int n = 0;
+      for (int b = 0; b < g.nb; b++) {
+        const int w = g.band_start[b + 1] - g.band_start[b];
+        n += w > 0 ? (w + task_bins - 1) / task_bins : 1;
+      }
+      if (n <= kMaxBandTasks) break;
+      task_bins *= 2;
+    }
+    int t = 0;
+    for (int b = 0; b < g.nb; b++) {
+      g.band_task0[b] = (short)t;
+      const int w = g.band_start[b + 1] - g.band_start[b];
+      const int n = w > 0 ? (w + task_bins - 1) / task_bins : 1;
+      for (int s2 = 0; s2 < n; s2++) {
+        g.task_band[t] = (short)b;
+        g.task_k[t] = g.band_start[b] + s2 * task_bins;
+        t++;
+      }
+    }
+    g.band_task0[g.nb] = (short)t;
+    g.task_k[t] = g.band_start[g.nb];
+    g.ntask = t;
+  }
   // temporal masking decays (masking_estimator.c:146-160)
   const float hop_time = (float)g.N / (4.0f * (float)sample_rate);
   for (int b = 0; b < g.nb; b++) {
