@@ -186,43 +186,75 @@ tonal_mask_direct_kernel(const GeoK g, const float* __restrict__ det, int det_st
   mask[(size_t)row * mask_stride + k] = m;
 }
 
-// Whitening weights: smooth3(noise) -> median (bitonic sort) -> power-law weights.
+// Whitening weights (spectral_whitening.c:59-111): smooth3(noise) -> median = sorted[K/2] ->
+// power-law weights.  The reference qsorts the K values for the one order statistic it needs;
+// here it is a 4-pass radix select on the float bit patterns (order-preserving for the
+// non-negative smoothed noise; negative / NaN inputs would order as their raw bits), exact
+// and O(K) instead of the 66 barrier-separated stages of a bitonic sort.
 __global__ void __launch_bounds__(512)
 whitening_kernel(const GeoK g, const float* __restrict__ noise, int noise_stride, float whit,
-                 float* __restrict__ wt, int wt_stride, int P2) {
+                 float* __restrict__ wt, int wt_stride) {
   extern __shared__ float sm[];
-  float* srt = sm;           // [P2]
-  float* smo = sm + P2;      // [K]
+  float* smo = sm;                                   // [K]
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sel_prefix, sel_rank;
   const int row = blockIdx.x;
   const float* __restrict__ n = noise + (size_t)row * noise_stride;
   const int K = g.K;
   const float f = 0.5f;
-  for (int k = threadIdx.x; k < P2; k += blockDim.x) {
-    float v = INFINITY;
-    if (k < K) {
-      const float c = n[k];
-      if (K < 2) v = c;
-      else if (k == 0) v = ((c + n[1]) / 2.0f * f) + (c * (1.0f - f));
-      else if (k == K - 1) v = (((n[K - 2] + c) / 2.0f) * f) + (c * (1.0f - f));
-      else v = (((n[k - 1] + c + n[k + 1]) / 3.0f) * f) + (c * (1.0f - f));
-      smo[k] = v;
-    }
-    srt[k] = v;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float c = n[k];
+    float v;
+    if (K < 2) v = c;
+    else if (k == 0) v = ((c + n[1]) / 2.0f * f) + (c * (1.0f - f));
+    else if (k == K - 1) v = (((n[K - 2] + c) / 2.0f) * f) + (c * (1.0f - f));
+    else v = (((n[k - 1] + c + n[k + 1]) / 3.0f) * f) + (c * (1.0f - f));
+    smo[k] = v;
+  }
+  if (threadIdx.x == 0) {
+    sel_prefix = 0u;
+    sel_rank = (unsigned)(K / 2);
   }
   __syncthreads();
-  for (int size = 2; size <= P2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < P2 / 2; t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const float a = srt[lo], b = srt[hi];
-        if ((a > b) == up) { srt[lo] = b; srt[hi] = a; }
-      }
-      __syncthreads();
+  for (int pass = 3; pass >= 0; pass--) {
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned prefix = sel_prefix;
+    const int shift = 8 * pass;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const unsigned bits = __float_as_uint(smo[k]);
+      // keys agreeing with the digits already fixed (the higher passes)
+      if (pass == 3 || (bits >> (shift + 8)) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
     }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // bucket whose cumulative count crosses the wanted rank: 8 buckets per lane + warp scan
+      const unsigned lane = threadIdx.x;
+      unsigned local[8], tot = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { local[i] = hist[8 * lane + i]; tot += local[i]; }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += y;
+      }
+      const unsigned before = incl - tot, r = sel_rank;
+      if (r >= before && r < incl) {                 // exactly one lane
+        unsigned acc = before;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (r >= acc && r < acc + local[i]) {
+            sel_prefix = (prefix << 8) | (8u * lane + (unsigned)i);
+            sel_rank = r - acc;
+          }
+          acc += local[i];
+        }
+      }
+    }
+    __syncthreads();
   }
-  float anchor = srt[K / 2];
+  float anchor = __uint_as_float(sel_prefix);
   if (anchor < kSpectralEps) anchor = kSpectralEps;
   for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
     float w = 1.0f;
@@ -770,13 +802,11 @@ bool launch_whitening(const GeoK& g, const float* noise, int noise_stride, int r
                       float whitening, float* wt, cudaStream_t st) {
   KTimer kt_(kcWhiten, st);
   if (rows <= 0) return true;
-  int P2 = 1;
-  while (P2 < g.K) P2 <<= 1;
-  const size_t smem = sizeof(float) * (size_t)(P2 + g.K);
+  const size_t smem = sizeof(float) * (size_t)g.K;
   if (smem > 48 * 1024)
     SB_CUDA(cudaFuncSetAttribute((const void*)whitening_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  whitening_kernel<<<rows, 512, smem, st>>>(g, noise, noise_stride, whitening, wt, g.Kp, P2);
+  whitening_kernel<<<rows, 512, smem, st>>>(g, noise, noise_stride, whitening, wt, g.Kp);
   SB_LAUNCH_CHECK();
   return true;
 }
