@@ -503,11 +503,11 @@ constexpr int kRsTile = 64;      // frames per tile
 constexpr int kRsRing = 5;       // tiles resident in shared memory
 constexpr int kRsAhead = 3;      // prefetch distance (tiles)
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -519,22 +519,35 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 rowscan_kernel(int ncols, int pitch, int rows, const float* A, float* B,   // B may alias A
                const RsCoef coef, float* __restrict__ state) {
-  __shared__ float ring[kRsRing][kRsTile][32];
+  __shared__ __align__(16) float ring[kRsRing][kRsTile][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 32 + lane;
   const bool cv = col < ncols;
   const int ntiles = (rows + kRsTile - 1) / kRsTile;
   constexpr int kMovers = 7;
 
-  // movers: rows of a tile are dealt round-robin to warps 1..7
+  // movers (warps 1..7): 16-byte vectors, 8 lanes per 32-column row, 4 rows per warp
+  // instruction.  Rows are Kp-pitched (Kp % 4 == 0), so whole vectors are always in bounds.
+  const int mrow = lane >> 3, mvec = (lane & 7) * 4;
+  const bool mv = blockIdx.x * 32 + mvec < pitch && blockIdx.x * 32 + mvec < ((ncols + 3) & ~3);
+  const float* Ab = A + blockIdx.x * 32 + mvec;
+  float* Bb = B + blockIdx.x * 32 + mvec;
   auto load_tile = [&](int t) {
     if (warp > 0 && t < ntiles) {
-      for (int r = warp - 1; r < kRsTile; r += kMovers) {
+      for (int r = 4 * (warp - 1) + mrow; r < kRsTile; r += 4 * kMovers) {
         const int f = t * kRsTile + r;
-        if (f < rows && cv) cp_async4(&ring[t % kRsRing][r][lane], A + (size_t)f * pitch + col);
+        if (f < rows && mv) cp_async16(&ring[t % kRsRing][r][mvec], Ab + (size_t)f * pitch);
       }
     }
     cp_async_commit();
+  };
+  auto store_tile = [&](int tb) {
+    for (int r = 4 * (warp - 1) + mrow; r < kRsTile; r += 4 * kMovers) {
+      const int f = tb * kRsTile + r;
+      if (f < rows && mv)
+        *reinterpret_cast<float4*>(Bb + (size_t)f * pitch) =
+            *reinterpret_cast<const float4*>(&ring[tb % kRsRing][r][mvec]);
+    }
   };
   float m = 0.f, c = 0.f;
   if (warp == 0 && cv) {
@@ -556,26 +569,13 @@ rowscan_kernel(int ncols, int pitch, int rows, const float* A, float* B,   // B 
         else m = fmaf(c, m, v);
         tp[r * 32] = m;
       }
-    } else {
-      // write back tile t-1 (finished in the previous iteration), then prefetch
-      if (t > 0) {
-        const int tb = t - 1;
-        for (int r = warp - 1; r < kRsTile; r += kMovers) {
-          const int f = tb * kRsTile + r;
-          if (f < rows && cv) B[(size_t)f * pitch + col] = ring[tb % kRsRing][r][lane];
-        }
-      }
+    } else if (t > 0) {
+      store_tile(t - 1);                     // finished in the previous iteration
     }
     load_tile(t + kRsAhead);
   }
   __syncthreads();
-  if (warp > 0 && ntiles > 0) {
-    const int tb = ntiles - 1;
-    for (int r = warp - 1; r < kRsTile; r += kMovers) {
-      const int f = tb * kRsTile + r;
-      if (f < rows && cv) B[(size_t)f * pitch + col] = ring[tb % kRsRing][r][lane];
-    }
-  }
+  if (warp > 0 && ntiles > 0) store_tile(ntiles - 1);
   if (warp == 0 && cv) state[col] = m;
 }
 
@@ -588,31 +588,36 @@ constexpr int kRs1Tile = 32, kRs1Ring = 5, kRs1Ahead = 3;
 __global__ void __launch_bounds__(256)
 rowscan1d_kernel(int ncols, int pitch, int rows, float smoothing, const float* P,
                  const float* noise, float* Mg, float* stable, float* st_state, float* sp_state) {
-  __shared__ float ringP[kRs1Ring][kRs1Tile][32];
-  __shared__ float ringN[kRs1Ring][kRs1Tile][32];
+  __shared__ __align__(16) float ringP[kRs1Ring][kRs1Tile][32];
+  __shared__ __align__(16) float ringN[kRs1Ring][kRs1Tile][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 32 + lane;
   const bool cv = col < ncols;
   const int ntiles = (rows + kRs1Tile - 1) / kRs1Tile;
   constexpr int kMovers = 7;
+  const int mrow = lane >> 3, mvec = (lane & 7) * 4;
+  const bool mv = blockIdx.x * 32 + mvec < pitch && blockIdx.x * 32 + mvec < ((ncols + 3) & ~3);
+  const size_t cb = (size_t)blockIdx.x * 32 + mvec;
   auto load_tile = [&](int t) {
     if (warp > 0 && t < ntiles) {
-      for (int r = warp - 1; r < kRs1Tile; r += kMovers) {
+      for (int r = 4 * (warp - 1) + mrow; r < kRs1Tile; r += 4 * kMovers) {
         const int f = t * kRs1Tile + r;
-        if (f < rows && cv) {
-          cp_async4(&ringP[t % kRs1Ring][r][lane], P + (size_t)f * pitch + col);
-          cp_async4(&ringN[t % kRs1Ring][r][lane], noise + (size_t)f * pitch + col);
+        if (f < rows && mv) {
+          cp_async16(&ringP[t % kRs1Ring][r][mvec], P + (size_t)f * pitch + cb);
+          cp_async16(&ringN[t % kRs1Ring][r][mvec], noise + (size_t)f * pitch + cb);
         }
       }
     }
     cp_async_commit();
   };
   auto store_tile = [&](int tb) {
-    for (int r = warp - 1; r < kRs1Tile; r += kMovers) {
+    for (int r = 4 * (warp - 1) + mrow; r < kRs1Tile; r += 4 * kMovers) {
       const int f = tb * kRs1Tile + r;
-      if (f < rows && cv) {
-        Mg[(size_t)f * pitch + col] = ringP[tb % kRs1Ring][r][lane];
-        stable[(size_t)f * pitch + col] = ringN[tb % kRs1Ring][r][lane];
+      if (f < rows && mv) {
+        *reinterpret_cast<float4*>(Mg + (size_t)f * pitch + cb) =
+            *reinterpret_cast<const float4*>(&ringP[tb % kRs1Ring][r][mvec]);
+        *reinterpret_cast<float4*>(stable + (size_t)f * pitch + cb) =
+            *reinterpret_cast<const float4*>(&ringN[tb % kRs1Ring][r][mvec]);
       }
     }
   };
