@@ -33,6 +33,22 @@ static const float kBark[25] = {100.f,  200.f,  300.f,  400.f,  510.f,  630.f,  
                                 2700.f, 3150.f, 3700.f, 4400.f, 5300.f, 6400.f, 7700.f,
                                 9500.f, 12000.f, 15500.f, 19000.f};
 
+static void fill_passes(GeoK& g) {
+  int len = g.M, s = 1;
+  for (int f = 0; f < g.nfac; f++) {
+    const int r = g.fac[f];
+    g.pass_l[f] = len / r;
+    g.pass_s[f] = s;
+    g.pass_tstep[f] = g.M / len;
+    g.pass_nbf[f] = g.M / r;
+    g.pass_smagic[f] = (unsigned)((0x100000000ull + (unsigned long long)s - 1) / (unsigned long long)s);
+    g.pass_nbfmagic[f] = (unsigned)((0x100000000ull + (unsigned long long)g.pass_nbf[f] - 1) /
+                                    (unsigned long long)g.pass_nbf[f]);
+    len /= r;
+    s *= r;
+  }
+}
+
 static void factorize(int m, int* fac, int* nfac) {
   int n = 0;
   while (m % 4 == 0) { fac[n++] = 4; m /= 4; }
@@ -125,6 +141,7 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
   g.cp = (int)(N / 2 - frame / 2);
   g.frame_p = (g.frame + 3) & ~3;
   factorize(g.M, g.fac, &g.nfac);
+  fill_passes(g);
 
   // periodic Hann over `frame` (spectral_utils.c:34-37, general_utils.c:26-31)
   const float pi = 3.14159265358979323846f;
@@ -274,6 +291,7 @@ Geometry* make_fft_geometry(int fft_size) {
   g.frame_p = (g.frame + 3) & ~3;
   g.scale = 1.0f;
   factorize(g.M, g.fac, &g.nfac);
+  fill_passes(g);
   std::vector<float> win(fft_size, 1.0f);
   std::vector<float2> tw(g.M), twn(g.M + 1);
   for (int k = 0; k < g.M; k++) {

@@ -33,15 +33,16 @@ template <bool INV>
 __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
   const int M = g.M;
   const float2* __restrict__ tw = g.tw;
-  int len = M;
-  int s = 1;
   for (int f = 0; f < g.nfac; f++) {
     const int r = g.fac[f];
-    const int l = len / r;
-    const int tstep = M / len;
+    const int l = g.pass_l[f];
+    const int s = g.pass_s[f];
+    const int tstep = g.pass_tstep[f];
+    const int nbf = g.pass_nbf[f];               // butterflies of this pass: M / r
+    const unsigned smagic = g.pass_smagic[f];    // j = idx / s without a division (idx < M <= 2^16)
     if (r == 4) {
-      for (int idx = threadIdx.x; idx < M / 4; idx += blockDim.x) {
-        const int j = idx / s;
+      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
         const int q = idx - j * s;
         const float2 a = x[q + s * j];
         const float2 b = x[q + s * (j + l)];
@@ -62,8 +63,8 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
         o[3 * s] = cmul(csub(amc, jb), w3);
       }
     } else if (r == 2) {
-      for (int idx = threadIdx.x; idx < M / 2; idx += blockDim.x) {
-        const int j = idx / s;
+      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
         const int q = idx - j * s;
         const float2 a = x[q + s * j];
         const float2 b = x[q + s * (j + l)];
@@ -76,8 +77,8 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
       // 5-point DFT from the symmetric / antisymmetric pairs (x1 +- x4, x2 +- x3)
       const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
       const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
-      for (int idx = threadIdx.x; idx < M / 5; idx += blockDim.x) {
-        const int j = idx / s;
+      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
         const int q = idx - j * s;
         const float2 x0 = x[q + s * j];
         const float2 x1 = x[q + s * (j + l)];
@@ -106,8 +107,8 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
       }
     } else if (r == 3) {
       const float h3 = 0.86602540378443865f;   // sin(2pi/3)
-      for (int idx = threadIdx.x; idx < M / 3; idx += blockDim.x) {
-        const int j = idx / s;
+      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
         const int q = idx - j * s;
         const float2 x0 = x[q + s * j];
         const float2 x1 = x[q + s * (j + l)];
@@ -131,11 +132,11 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
       // needs only a few distinct roots per term (the root loads were the bottleneck of the
       // radix-167 pass of N = 3006 when every lane asked for a different one)
       const double2* __restrict__ root = g.twg + g.twg_off[f];
-      const int nbf = M / r;
+      const unsigned nbfmagic = g.pass_nbfmagic[f];
       for (int item = threadIdx.x; item < M; item += blockDim.x) {
-        const int t = item / nbf;        // output index inside the butterfly
-        const int idx = item - t * nbf;  // butterfly
-        const int j = idx / s;
+        const int t = nbf == 1 ? item : (int)__umulhi((unsigned)item, nbfmagic);   // output index
+        const int idx = item - t * nbf;                           // butterfly
+        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
         const int q = idx - j * s;
         const float2 v0 = x[q + s * j];
         double ar = (double)v0.x, ai = (double)v0.y;
@@ -158,8 +159,6 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
     }
     __syncthreads();
     float2* tmp = x; x = y; y = tmp;
-    len = l;
-    s *= r;
   }
   return x;
 }
