@@ -20,13 +20,14 @@
 //       i.e. ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)): 3 FADD per candidate and row;
 //     * the 7 dt that wrap (-16..-13, 2..4) need two lags per row and keep the 8
 //       targets in flight in registers (r0+r1+...+r7 in order).
-//   Units are dealt to warps so that each SM sub-partition gets the same work.
+//   Units come from a per-CTA queue (wrapping dt first, the last plain dt split in two target
+//   halves), so a warp that finishes early takes the next one.
 //   Pass 1 outputs, per (target, block), a 357-bit field of the candidates that pass the
 //   hard threshold d <= 4 h_b^2 (a few percent, nlm_filter_avx.c:208-212) and, for each of
 //   them, its weight at a fixed scratch address W[target][block][candidate] -- every
 //   (target, block, candidate) has exactly one owner lane, so the scratch content does
-//   not depend on scheduling.  Targets are processed in chunks of 1024 so that the
-//   scratch (a few MB touched) stays in L2.
+//   not depend on scheduling.  Targets are processed in chunks of ~2k (whole waves of CTAs on
+//   the device's SMs) so that most of the touched scratch (tens of MB) stays in L2.
 // Pass 2 (nlm3_paste_kernel): 8 lanes per (target, block) walk the bit field and paste the
 //   flagged candidates in the reference's (dt, df) order.  Deterministic and independent
 //   of how the targets are tiled, so streaming stays bit-exact.
