@@ -413,11 +413,14 @@ nlm3_paste_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int
       while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1;
-        const float wgt = (dti == kNlmPast && bit == kNlmRangeFreq) ? w_self : wrow[bit];
+        // both loads are issued before either is used: one L2 round trip per candidate
+        int c = bs + j + bit - kNlmRangeFreq;          // bin clamp(bs + j + df)
+        c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
+        const float v = __ldg(prow + c);
+        float wgt = __ldg(wrow + bit);
+        if (dti == kNlmPast && bit == kNlmRangeFreq) wgt = w_self;
         if (!(wgt < kNlmMinWeight)) {                  // nlm_filter_avx.c:219-221
-          int c = bs + j + bit - kNlmRangeFreq;        // bin clamp(bs + j + df)
-          c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
-          acc = fmaf(wgt, prow[c], acc);
+          acc = fmaf(wgt, v, acc);
           ws += wgt;
         }
       }
