@@ -385,3 +385,24 @@ def test_full_size_properties_config5(gpu, ref):
 def test_smoke_entry_point(gpu):
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_older_nlm_kernels_still_match_golden(variant):
+    """SB_NLM_KERNEL=1 (direct form, reference accumulation order) and =2 (row-SSD sharing with
+    producer/reducer warps) stay selectable for A/B measurements; both must keep parity."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from libspecbleach_b200 import api; from common import load_golden\n"
+        "g = load_golden('nlm_module'); out = api.debug_nlm(g['snr'], float(g['h']))\n"
+        "err = float(np.abs(out[20:] - g['out']).max()); print('ERR', err)\n"
+        "sys.exit(0 if err <= 1e-5 * max(1.0, float(np.abs(g['out']).max())) else 1)\n"
+    ) % (str(root), str(root / "tests"))
+    env = dict(os.environ, SB_NLM_KERNEL=variant)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
