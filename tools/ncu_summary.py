@@ -1,5 +1,6 @@
 """Condense `ncu --page raw --csv` / `--page source --csv` exports into the handful of
-numbers DESIGN.md and profiles/ quote.  usage: ncu_summary.py raw.csv [src.csv]"""
+numbers DESIGN.md and profiles/ quote.  usage: ncu_summary.py raw.csv [src.csv]
+       ncu_summary.py --launches launches.csv '<the ncu command line>'"""
 import collections
 import csv
 import sys
@@ -58,10 +59,6 @@ def src(path, top=14):
               f"avg active threads {thr[op] / max(n, 1):4.1f}")
 
 
-if __name__ == "__main__":
-    raw(sys.argv[1])
-    if len(sys.argv) > 2:
-        src(sys.argv[2])
 
 
 def by_line(path, top=30):
@@ -90,3 +87,29 @@ def by_line(path, top=30):
     print(f"total warp instructions {tot}, samples {ts}")
     for ln, (n, sm) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         print(f"  {ln:4d} {100 * n / tot:5.1f}% instr {100 * sm / max(ts, 1):5.1f}% samples | {src[ln].strip()[:88]}")
+
+
+def launches(path, title=""):
+    """`ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel and its
+    share of the captured launches (cold-cache, serialised: shares, not absolutes)."""
+    import re
+    rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[12] == "gpu__time_duration.sum"]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        name = re.sub(r"^.*::", "", r[4].split("(")[0])
+        agg[name][0] += 1
+        agg[name][1] += float(r[14]) / 1e3
+    tot = sum(v[1] for v in agg.values())
+    print(title)
+    print(f"(cold-cache, serialised launches: compare SHARES)  launches {len(rows)}, total {tot:.0f} us")
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{name:26s} n={n:4d} total {us:9.1f} us {100 * us / tot:5.1f}%  avg {us / n:8.1f} us")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "--launches":
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    else:
+        raw(sys.argv[1])
+        if len(sys.argv) > 2:
+            src(sys.argv[2])
