@@ -75,6 +75,7 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   // s = product of the previous radices, twiddle step M/len, nbf = M/r and ceil(2^32/s), nbf
   int pass_l[14], pass_s[14], pass_tstep[14], pass_nbf[14];
   unsigned pass_smagic[14], pass_nbfmagic[14];
+  int fft_threads;            // CTA size of the FFT kernels (fill_passes: fewest idle warp rounds)
   int nb;                                // number of Bark bands (<= 25)
   int band_start[kMaxBands + 1];         // band b = [band_start[b], band_start[b+1])
   // Bark bands differ wildly in width (3 bins ... two thirds of the spectrum): per-frame band

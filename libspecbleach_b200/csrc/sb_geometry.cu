@@ -47,6 +47,34 @@ static void fill_passes(GeoK& g) {
     len /= r;
     s *= r;
   }
+  // CTA size of the FFT kernels: the passes have M / r butterflies each, which 256 threads
+  // rarely divide (M = 1600: 400 and 320 -> every second round half empty).  Take the size
+  // with the fewest warp rounds over all passes and the load / split loops, among those that
+  // keep >= 24 warps resident per SM (2 x 8M bytes of shared memory and ~56 registers).
+  double best = 1e30;
+  g.fft_threads = 256;
+  for (int T = 96; T <= 512; T += 8) {
+    const int warps = (T + 31) / 32;
+    double cost = 0.0;
+    for (int f = 0; f < g.nfac; f++) {
+      const int r = g.fac[f];
+      const bool hard = r == 2 || r == 3 || r == 4 || r == 5;
+      const int items = hard ? g.pass_nbf[f] : g.M;
+      cost += (double)((items + T - 1) / T) * warps * (hard ? r : 2.0 * r);
+    }
+    cost += 2.0 * (double)((g.M + T - 1) / T) * warps * 2.0;      // load and split / crop loops
+    cost += 0.25 * g.nfac * warps;                                 // barrier per pass
+    const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
+    int ctas = (int)((227 * 1024) / (smem + 1024));
+    const int by_regs = 65536 / (56 * warps * 32);
+    if (by_regs < ctas) ctas = by_regs;
+    if (ctas > 32) ctas = 32;
+    if (ctas < 1) ctas = 1;
+    const int resident = ctas * warps;
+    if (resident < 24) cost *= 24.0 / resident;
+    if (cost < best - 1e-9) { best = cost; g.fft_threads = T; }
+  }
+  if (const char* e = getenv("SB_FFT_THREADS")) g.fft_threads = atoi(e);
 }
 
 static void factorize(int m, int* fac, int* nfac) {

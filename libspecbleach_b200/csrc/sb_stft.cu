@@ -19,7 +19,7 @@ namespace sb {
 
 namespace {
 
-constexpr int kFftThreads = 256;
+constexpr int kFftMaxThreads = 512;   // the launch uses g.fft_threads (sb_geometry.cu)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -29,6 +29,145 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 
 // Mixed-radix Stockham DIF passes over M complex points held in shared memory.
 // Returns the buffer that holds the result.  INV conjugates every twiddle.
+//
+// Pass f (radix r, s = product of the radices before it, l = M / (r s), nbf = M / r
+// butterflies): butterfly idx = j s + q reads x[idx + k nbf] (k < r; s l == nbf) and writes
+// y[idx + j s (r - 1) + k s] after a twist by tw[k j tstep].  In the last pass l == 1, so
+// j == 0 and every twist is 1: LAST drops the loads and the multiplies.
+template <bool INV, bool LAST>
+__device__ __forceinline__ void pass_radix4(const float2* __restrict__ x, float2* __restrict__ y,
+                                            const float2* __restrict__ tw, int nbf, int s,
+                                            int tstep, unsigned smagic) {
+  const int sr1 = 3 * s;
+  for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+    const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
+    const float2* xp = x + idx;
+    const float2 a = xp[0];
+    const float2 b = xp[nbf];
+    const float2 c = xp[2 * nbf];
+    const float2 d = xp[3 * nbf];
+    const float2 apc = cadd(a, c), amc = csub(a, c);
+    const float2 bpd = cadd(b, d), bmd = csub(b, d);
+    // forward: -i*(b-d); inverse: +i*(b-d)
+    const float2 jb = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);
+    float2* o = y + idx + j * sr1;
+    if (LAST) {
+      o[0] = cadd(apc, bpd);
+      o[s] = cadd(amc, jb);
+      o[2 * s] = csub(apc, bpd);
+      o[3 * s] = csub(amc, jb);
+    } else {
+      const int jt = j * tstep;
+      float2 w1 = __ldg(&tw[jt]);
+      float2 w2 = __ldg(&tw[2 * jt]);
+      float2 w3 = __ldg(&tw[3 * jt]);
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      o[0] = cadd(apc, bpd);
+      o[s] = cmul(cadd(amc, jb), w1);
+      o[2 * s] = cmul(csub(apc, bpd), w2);
+      o[3 * s] = cmul(csub(amc, jb), w3);
+    }
+  }
+}
+
+template <bool INV, bool LAST>
+__device__ __forceinline__ void pass_radix2(const float2* __restrict__ x, float2* __restrict__ y,
+                                            const float2* __restrict__ tw, int nbf, int s,
+                                            int tstep, unsigned smagic) {
+  for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+    const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
+    const float2 a = x[idx];
+    const float2 b = x[idx + nbf];
+    float2* o = y + idx + j * s;
+    o[0] = cadd(a, b);
+    if (LAST) {
+      o[s] = csub(a, b);
+    } else {
+      float2 w1 = __ldg(&tw[j * tstep]);
+      if (INV) w1.y = -w1.y;
+      o[s] = cmul(csub(a, b), w1);
+    }
+  }
+}
+
+// 5-point DFT from the symmetric / antisymmetric pairs (x1 +- x4, x2 +- x3)
+template <bool INV, bool LAST>
+__device__ __forceinline__ void pass_radix5(const float2* __restrict__ x, float2* __restrict__ y,
+                                            const float2* __restrict__ tw, int nbf, int s,
+                                            int tstep, unsigned smagic) {
+  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
+  const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
+  const int sr1 = 4 * s;
+  for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+    const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
+    const float2* xp = x + idx;
+    const float2 x0 = xp[0];
+    const float2 x1 = xp[nbf];
+    const float2 x2 = xp[2 * nbf];
+    const float2 x3 = xp[3 * nbf];
+    const float2 x4 = xp[4 * nbf];
+    const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+    const float2 a1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+    const float2 a2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+    const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+    const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+    // forward: y1 = a1 - i b1, y4 = a1 + i b1, y2 = a2 - i b2, y3 = a2 + i b2; inverse: conjugate roots
+    const float2 ib1 = INV ? make_float2(-b1.y, b1.x) : make_float2(b1.y, -b1.x);
+    const float2 ib2 = INV ? make_float2(-b2.y, b2.x) : make_float2(b2.y, -b2.x);
+    float2* o = y + idx + j * sr1;
+    o[0] = cadd(x0, cadd(t1, t2));
+    if (LAST) {
+      o[s] = cadd(a1, ib1);
+      o[2 * s] = cadd(a2, ib2);
+      o[3 * s] = csub(a2, ib2);
+      o[4 * s] = csub(a1, ib1);
+    } else {
+      const int jt = j * tstep;
+      float2 w1 = __ldg(&tw[jt]);
+      float2 w2 = __ldg(&tw[2 * jt]);
+      float2 w3 = __ldg(&tw[3 * jt]);
+      float2 w4 = __ldg(&tw[4 * jt]);
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
+      o[s] = cmul(cadd(a1, ib1), w1);
+      o[2 * s] = cmul(cadd(a2, ib2), w2);
+      o[3 * s] = cmul(csub(a2, ib2), w3);
+      o[4 * s] = cmul(csub(a1, ib1), w4);
+    }
+  }
+}
+
+template <bool INV, bool LAST>
+__device__ __forceinline__ void pass_radix3(const float2* __restrict__ x, float2* __restrict__ y,
+                                            const float2* __restrict__ tw, int nbf, int s,
+                                            int tstep, unsigned smagic) {
+  const float h3 = 0.86602540378443865f;   // sin(2pi/3)
+  const int sr1 = 2 * s;
+  for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
+    const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
+    const float2* xp = x + idx;
+    const float2 x0 = xp[0];
+    const float2 x1 = xp[nbf];
+    const float2 x2 = xp[2 * nbf];
+    const float2 t1 = cadd(x1, x2), t3 = csub(x1, x2);
+    const float2 a = make_float2(x0.x - 0.5f * t1.x, x0.y - 0.5f * t1.y);
+    const float2 b = make_float2(h3 * t3.x, h3 * t3.y);
+    const float2 ib = INV ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
+    float2* o = y + idx + j * sr1;
+    o[0] = cadd(x0, t1);
+    if (LAST) {
+      o[s] = cadd(a, ib);
+      o[2 * s] = csub(a, ib);
+    } else {
+      const int jt = j * tstep;
+      float2 w1 = __ldg(&tw[jt]);
+      float2 w2 = __ldg(&tw[2 * jt]);
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
+      o[s] = cmul(cadd(a, ib), w1);
+      o[2 * s] = cmul(csub(a, ib), w2);
+    }
+  }
+}
+
 template <bool INV>
 __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
   const int M = g.M;
@@ -40,91 +179,19 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
     const int tstep = g.pass_tstep[f];
     const int nbf = g.pass_nbf[f];               // butterflies of this pass: M / r
     const unsigned smagic = g.pass_smagic[f];    // j = idx / s without a division (idx < M <= 2^16)
+    const bool last = l == 1;
     if (r == 4) {
-      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
-        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
-        const int q = idx - j * s;
-        const float2 a = x[q + s * j];
-        const float2 b = x[q + s * (j + l)];
-        const float2 c = x[q + s * (j + 2 * l)];
-        const float2 d = x[q + s * (j + 3 * l)];
-        const float2 apc = cadd(a, c), amc = csub(a, c);
-        const float2 bpd = cadd(b, d), bmd = csub(b, d);
-        // forward: -i*(b-d); inverse: +i*(b-d)
-        const float2 jb = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);
-        float2 w1 = __ldg(&tw[j * tstep]);
-        float2 w2 = __ldg(&tw[2 * j * tstep]);
-        float2 w3 = __ldg(&tw[3 * j * tstep]);
-        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-        float2* o = &y[q + s * (4 * j)];
-        o[0] = cadd(apc, bpd);
-        o[s] = cmul(cadd(amc, jb), w1);
-        o[2 * s] = cmul(csub(apc, bpd), w2);
-        o[3 * s] = cmul(csub(amc, jb), w3);
-      }
+      if (last) pass_radix4<INV, true>(x, y, tw, nbf, s, tstep, smagic);
+      else pass_radix4<INV, false>(x, y, tw, nbf, s, tstep, smagic);
     } else if (r == 2) {
-      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
-        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
-        const int q = idx - j * s;
-        const float2 a = x[q + s * j];
-        const float2 b = x[q + s * (j + l)];
-        float2 w1 = __ldg(&tw[j * tstep]);
-        if (INV) w1.y = -w1.y;
-        y[q + s * (2 * j)] = cadd(a, b);
-        y[q + s * (2 * j + 1)] = cmul(csub(a, b), w1);
-      }
+      if (last) pass_radix2<INV, true>(x, y, tw, nbf, s, tstep, smagic);
+      else pass_radix2<INV, false>(x, y, tw, nbf, s, tstep, smagic);
     } else if (r == 5) {
-      // 5-point DFT from the symmetric / antisymmetric pairs (x1 +- x4, x2 +- x3)
-      const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
-      const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
-      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
-        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
-        const int q = idx - j * s;
-        const float2 x0 = x[q + s * j];
-        const float2 x1 = x[q + s * (j + l)];
-        const float2 x2 = x[q + s * (j + 2 * l)];
-        const float2 x3 = x[q + s * (j + 3 * l)];
-        const float2 x4 = x[q + s * (j + 4 * l)];
-        const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-        const float2 a1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-        const float2 a2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-        const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-        const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-        // forward: y1 = a1 - i b1, y4 = a1 + i b1, y2 = a2 - i b2, y3 = a2 + i b2; inverse: conjugate roots
-        const float2 ib1 = INV ? make_float2(-b1.y, b1.x) : make_float2(b1.y, -b1.x);
-        const float2 ib2 = INV ? make_float2(-b2.y, b2.x) : make_float2(b2.y, -b2.x);
-        float2 w1 = __ldg(&tw[j * tstep]);
-        float2 w2 = __ldg(&tw[2 * j * tstep]);
-        float2 w3 = __ldg(&tw[3 * j * tstep]);
-        float2 w4 = __ldg(&tw[4 * j * tstep]);
-        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
-        float2* o = &y[q + s * (5 * j)];
-        o[0] = cadd(x0, cadd(t1, t2));
-        o[s] = cmul(cadd(a1, ib1), w1);
-        o[2 * s] = cmul(cadd(a2, ib2), w2);
-        o[3 * s] = cmul(csub(a2, ib2), w3);
-        o[4 * s] = cmul(csub(a1, ib1), w4);
-      }
+      if (last) pass_radix5<INV, true>(x, y, tw, nbf, s, tstep, smagic);
+      else pass_radix5<INV, false>(x, y, tw, nbf, s, tstep, smagic);
     } else if (r == 3) {
-      const float h3 = 0.86602540378443865f;   // sin(2pi/3)
-      for (int idx = threadIdx.x; idx < nbf; idx += blockDim.x) {
-        const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
-        const int q = idx - j * s;
-        const float2 x0 = x[q + s * j];
-        const float2 x1 = x[q + s * (j + l)];
-        const float2 x2 = x[q + s * (j + 2 * l)];
-        const float2 t1 = cadd(x1, x2), t3 = csub(x1, x2);
-        const float2 a = make_float2(x0.x - 0.5f * t1.x, x0.y - 0.5f * t1.y);
-        const float2 b = make_float2(h3 * t3.x, h3 * t3.y);
-        const float2 ib = INV ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
-        float2 w1 = __ldg(&tw[j * tstep]);
-        float2 w2 = __ldg(&tw[2 * j * tstep]);
-        if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
-        float2* o = &y[q + s * (3 * j)];
-        o[0] = cadd(x0, t1);
-        o[s] = cmul(cadd(a, ib), w1);
-        o[2 * s] = cmul(csub(a, ib), w2);
-      }
+      if (last) pass_radix3<INV, true>(x, y, tw, nbf, s, tstep, smagic);
+      else pass_radix3<INV, false>(x, y, tw, nbf, s, tstep, smagic);
     } else {
       // generic radix: one work item per output point; the r-term sum runs in
       // double with double roots of unity and is rounded to float once
@@ -166,7 +233,7 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
 // ---------------------------------------------------------------------------
 // forward: frame f = xbuf[f*hop, f*hop+frame) -> Hann -> centre in N -> rFFT
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFftThreads)
+__global__ void __launch_bounds__(kFftMaxThreads)
 forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__ Xre,
                float* __restrict__ Xim, float* __restrict__ P) {
   extern __shared__ float2 smem[];
@@ -176,13 +243,22 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
   const float* __restrict__ src = xbuf + (size_t)f * g.hop;
   const float* __restrict__ win = g.win;
   // fft_load_input_samples + INPUT window (fft_transform.c:165-182, stft_windows.c:120-127)
-  for (int k = threadIdx.x; k < g.M; k += blockDim.x) {
-    const int i0 = 2 * k - g.cp;
-    const int i1 = i0 + 1;
-    float v0 = 0.f, v1 = 0.f;
-    if (i0 >= 0 && i0 < g.frame) v0 = src[i0] * __ldg(&win[i0]);
-    if (i1 >= 0 && i1 < g.frame) v1 = src[i1] * __ldg(&win[i1]);
-    a[k] = make_float2(v0, v1);
+  // four rounds of loads are requested before the first is used (one round per DRAM / L2
+  // latency otherwise: the runtime trip count keeps ptxas from batching them itself)
+  for (int k0 = threadIdx.x; k0 < g.M; k0 += 4 * blockDim.x) {
+    float v0[4], v1[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i0 = 2 * (k0 + u * (int)blockDim.x) - g.cp;
+      const int i1 = i0 + 1;
+      v0[u] = (i0 >= 0 && i0 < g.frame) ? src[i0] * __ldg(&win[i0]) : 0.f;
+      v1[u] = (i1 >= 0 && i1 < g.frame) ? src[i1] * __ldg(&win[i1]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = k0 + u * (int)blockDim.x;
+      if (k < g.M) a[k] = make_float2(v0[u], v1[u]);
+    }
   }
   __syncthreads();
   const float2* Z = stockham<false>(a, b, g);
@@ -217,7 +293,7 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
 // ---------------------------------------------------------------------------
 // inverse: Y -> unnormalised HC2R -> OUTPUT window / scale -> centre crop
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFftThreads)
+__global__ void __launch_bounds__(kFftMaxThreads)
 inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restrict__ Yim,
                float* __restrict__ synth) {
   extern __shared__ float2 smem[];
@@ -227,16 +303,29 @@ inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restr
   const int M = g.M;
   const float* __restrict__ re = Yre + (size_t)f * g.Kp;
   const float* __restrict__ im = Yim + (size_t)f * g.Kp;
-  for (int k = threadIdx.x; k < M; k += blockDim.x) {
-    float xr = re[k], xi = (k == 0) ? 0.f : im[k];
-    float yr = re[M - k], yi = (k == 0) ? 0.f : -im[M - k];   // conj X[M-k]
-    const float er = xr + yr, ei = xi + yi;
-    const float dr = xr - yr, di = xi - yi;
-    const float2 w = __ldg(&g.twn[k]);
-    // t = conj(w) * D ; Z = E + i*t
-    const float tr = dr * w.x + di * w.y;
-    const float ti = di * w.x - dr * w.y;
-    a[k] = make_float2(er - ti, ei + tr);
+  for (int k0 = threadIdx.x; k0 < M; k0 += 4 * blockDim.x) {   // loads batched as in forward_kernel
+    float xr[4], xi[4], yr[4], yi[4];
+    float2 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = k0 + u * (int)blockDim.x;
+      const bool in = k < M;
+      xr[u] = in ? re[k] : 0.f;
+      xi[u] = (in && k != 0) ? im[k] : 0.f;
+      yr[u] = in ? re[M - k] : 0.f;
+      yi[u] = (in && k != 0) ? -im[M - k] : 0.f;   // conj X[M-k]
+      w[u] = in ? __ldg(&g.twn[k]) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = k0 + u * (int)blockDim.x;
+      const float er = xr[u] + yr[u], ei = xi[u] + yi[u];
+      const float dr = xr[u] - yr[u], di = xi[u] - yi[u];
+      // t = conj(w) * D ; Z = E + i*t
+      const float tr = dr * w[u].x + di * w[u].y;
+      const float ti = di * w[u].x - dr * w[u].y;
+      if (k < M) a[k] = make_float2(er - ti, ei + tr);
+    }
   }
   __syncthreads();
   const float2* z = stockham<true>(a, b, g);
@@ -244,9 +333,15 @@ inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restr
   float* __restrict__ out = synth + (size_t)f * g.frame_p;
   const float* __restrict__ win = g.win;
   const float* zf = reinterpret_cast<const float*>(z);
+  // the quotient by the constant scale: reciprocal, one residual correction (the IEEE quotient
+  // for every normal operand; the generic division sequence was 12 % of this kernel)
+  const float scale = g.scale, inv_scale = 1.0f / scale;
+#pragma unroll 4
   for (int i = threadIdx.x; i < g.frame; i += blockDim.x) {
-    const float v = zf[g.cp + i];
-    out[i] = (v * __ldg(&win[i])) / g.scale;
+    const float num = zf[g.cp + i] * __ldg(&win[i]);
+    const float q0 = num * inv_scale;
+    const float rem = fmaf(-q0, scale, num);
+    out[i] = fmaf(rem, inv_scale, q0);
   }
 }
 
@@ -255,22 +350,26 @@ inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restr
 // the accumulator receives frames oldest first.  i runs over the n output
 // samples of this call followed by the `frame` samples of the new tail.
 // ---------------------------------------------------------------------------
+template <typename I>
 __global__ void ola_kernel(const GeoK g, const float* __restrict__ synth, int frames,
                            int carry, unsigned n, const float* __restrict__ tail_in,
                            float* __restrict__ tail_out, float* __restrict__ y) {
+  // I = int when n + frame + carry < 2^31 (the usual case), long long otherwise: the two
+  // divisions by hop per sample are what this kernel spends its time on
   const unsigned total = n + (unsigned)g.frame;
+  const I hop = (I)g.hop, frame = (I)g.frame;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += gridDim.x * blockDim.x) {
     float acc = (i < (unsigned)g.frame) ? tail_in[i] : 0.f;
-    const long long ic = (long long)i + carry;
-    long long fmax = ic / g.hop - 1;
-    if (fmax > frames - 1) fmax = frames - 1;
-    long long lo = ic - g.frame + 1;
-    long long fmin = lo <= 0 ? 0 : (lo + g.hop - 1) / g.hop - 1;
+    const I ic = (I)i + (I)carry;
+    I fmax = ic / hop - 1;
+    if (fmax > (I)frames - 1) fmax = (I)frames - 1;
+    const I lo = ic - frame + 1;
+    I fmin = lo <= 0 ? 0 : (lo + hop - 1) / hop - 1;
     if (fmin < 0) fmin = 0;
-    for (long long f = fmin; f <= fmax; f++) {
-      const long long o = (f + 1) * g.hop - carry;   // first output sample of frame f
-      acc += synth[(size_t)f * g.frame_p + (size_t)(i - o)];
+    for (I f = fmin; f <= fmax; f++) {
+      const I o = (f + 1) * hop - (I)carry;   // first output sample of frame f
+      acc += synth[(size_t)f * g.frame_p + (size_t)((I)i - o)];
     }
     if (i < n) y[i] = acc;
     else tail_out[i - n] = acc;
@@ -292,7 +391,7 @@ bool launch_forward(const GeoK& g, const float* xbuf, int frames, float* Xre, fl
   if (frames <= 0) return true;
   const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
   if (!set_fft_smem((const void*)forward_kernel, smem)) return false;
-  forward_kernel<<<frames, kFftThreads, smem, st>>>(g, xbuf, Xre, Xim, P);
+  forward_kernel<<<frames, g.fft_threads, smem, st>>>(g, xbuf, Xre, Xim, P);
   SB_LAUNCH_CHECK();
   return true;
 }
@@ -303,7 +402,7 @@ bool launch_inverse(const GeoK& g, const float* Yre, const float* Yim, int frame
   if (frames <= 0) return true;
   const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
   if (!set_fft_smem((const void*)inverse_kernel, smem)) return false;
-  inverse_kernel<<<frames, kFftThreads, smem, st>>>(g, Yre, Yim, frames ? synth : synth);
+  inverse_kernel<<<frames, g.fft_threads, smem, st>>>(g, Yre, Yim, synth);
   SB_LAUNCH_CHECK();
   return true;
 }
@@ -314,7 +413,10 @@ bool launch_ola(const GeoK& g, const float* synth, int frames, uint32_t carry, u
   const unsigned total = n + (unsigned)g.frame;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  ola_kernel<<<blocks, 256, 0, st>>>(g, synth, frames, (int)carry, n, tail_in, tail_out, y);
+  if ((unsigned long long)n + (unsigned long long)g.frame + carry + (unsigned long long)g.hop < 0x7fffffffull)
+    ola_kernel<int><<<blocks, 256, 0, st>>>(g, synth, frames, (int)carry, n, tail_in, tail_out, y);
+  else
+    ola_kernel<long long><<<blocks, 256, 0, st>>>(g, synth, frames, (int)carry, n, tail_in, tail_out, y);
   SB_LAUNCH_CHECK();
   return true;
 }
