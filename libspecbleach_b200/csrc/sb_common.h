@@ -98,6 +98,7 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   const float* abs_thr_spl;              // [Kp] absolute threshold, dB SPL
   const float* abs_thr_lin;              // [Kp] the same mapped back to power
   const int* cband;                      // [Kp] interpolation band of a bin
+  const float* veto_t;                   // [Kp] position of the bin between the centres of cband, cband + 1, clamped to [0, 1]
   const int* band_of_bin;                // [Kp] Bark band containing a bin
 };
 

@@ -54,18 +54,31 @@ __global__ void fill_rows_kernel(const GeoK g, const float* __restrict__ row,
   for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * g.Kp + k] = v;
 }
 
-__global__ void snr_kernel(const GeoK g, const float* __restrict__ P,
-                           const float* __restrict__ noise, float* __restrict__ S) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t o = (size_t)blockIdx.y * g.Kp + k;
-  if (k >= g.Kp) return;
-  float v = 0.f;
-  if (k < g.K) {
-    const float n = noise[o];
-    const float den = n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin;
-    v = P[o] / den;
+// The (frame, bin) elementwise kernels below run one CTA per frame row, a thread per group
+// of 4 bins (128-bit loads and stores; rows are Kp = 4-aligned floats from cudaMalloc), CTA
+// size = the row's quads rounded up to a warp (row_threads): a thread per bin on a 2D grid
+// reached ~45 % of the HBM rate, with a quarter of the lanes past the end of the row.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float snr_one(float p, float n, bool in) {
+  const float den = n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin;
+  return in ? p / den : 0.f;
+}
+
+__global__ void __launch_bounds__(512)
+snr_kernel(const GeoK g, const float* __restrict__ P, const float* __restrict__ noise,
+           float* __restrict__ S) {
+  const size_t ro = (size_t)blockIdx.x * g.Kp;
+  for (int k = 4 * threadIdx.x; k < g.Kp; k += 4 * blockDim.x) {
+    const float4 p = ld4(P + ro + k), n = ld4(noise + ro + k);
+    float4 v;
+    v.x = snr_one(p.x, n.x, k < g.K);
+    v.y = snr_one(p.y, n.y, k + 1 < g.K);
+    v.z = snr_one(p.z, n.z, k + 2 < g.K);
+    v.w = snr_one(p.w, n.w, k + 3 < g.K);
+    st4(S + ro + k, v);
   }
-  S[o] = v;
 }
 
 // 51-bin edge-clamped median over frequency, then the tonal mask
@@ -271,28 +284,17 @@ struct PreArgs {
   float alpha_max_user, tonal_gain;
 };
 
-__global__ void gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
-                                const float* __restrict__ noise_t,
-                                const float* __restrict__ mask, float* __restrict__ Mg,
-                                float* __restrict__ alpha, float* __restrict__ clean) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= g.Kp) return;
-  const int i = a.first_active + blockIdx.y;
-  const size_t o = (size_t)i * g.Kp + k;
-  if (k >= g.K) {
-    alpha[o] = 1.f;
-    if (a.two_d) { Mg[o] = 0.f; clean[o] = 0.f; }
-    return;
-  }
-  const float n = noise_t[o];
+// one bin; *mg and *cl are only meaningful in 2D
+__device__ __forceinline__ float pre_one(const PreArgs& a, float refv, float n, float m, float* mg,
+                                         float* cl) {
   float spec;
   if (a.two_d) {
     const float den = n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin;
-    spec = ref[o] * den;             // nlm_filter.c:481-508 (ref = smoothed SNR)
-    Mg[o] = spec;
-    clean[o] = fmaxf(spec - n, 0.0f);
+    spec = refv * den;               // nlm_filter.c:481-508 (ref = smoothed SNR)
+    *mg = spec;
+    *cl = fmaxf(spec - n, 0.0f);
   } else {
-    spec = ref[o];                   // 1D: alpha from the UNsmoothed power (spectral_denoiser.c:298-300)
+    spec = refv;                     // 1D: alpha from the UNsmoothed power (spectral_denoiser.c:298-300)
   }
   // suppression_engine.c:108-133
   const float snr_db = 10.0f * log10f(spec / (n + kSpectralEps));
@@ -305,7 +307,6 @@ __global__ void gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict
   }
   // tonal_reducer.c:92-113
   if (!(a.tonal_gain >= 0.999f)) {
-    const float m = mask[(size_t)i * a.mask_stride + k];
     if (m > 0.0f) {
       const float strength = 1.0f - a.tonal_gain;
       const float alpha_needed = kAlphaMin + (strength * (kAlphaMaxTonal - kAlphaMin));
@@ -313,7 +314,37 @@ __global__ void gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict
       al = fmaxf(al, target_alpha);
     }
   }
-  alpha[o] = al;
+  return al;
+}
+
+__global__ void __launch_bounds__(512)
+gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
+                const float* __restrict__ noise_t, const float* __restrict__ mask,
+                float* __restrict__ Mg, float* __restrict__ alpha, float* __restrict__ clean) {
+  const int i = a.first_active + blockIdx.x;
+  const size_t ro = (size_t)i * g.Kp;
+  const bool tonal = !(a.tonal_gain >= 0.999f);
+  const float* __restrict__ mrow = mask + (size_t)i * a.mask_stride;
+  for (int k = 4 * threadIdx.x; k < g.Kp; k += 4 * blockDim.x) {
+    const float4 r4 = ld4(ref + ro + k), n4 = ld4(noise_t + ro + k);
+    const float rv[4] = {r4.x, r4.y, r4.z, r4.w}, nv[4] = {n4.x, n4.y, n4.z, n4.w};
+    float al[4], mg[4], cl[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k + u < g.K) {
+        const float m = tonal ? mrow[k + u] : 0.f;
+        mg[u] = 0.f; cl[u] = 0.f;
+        al[u] = pre_one(a, rv[u], nv[u], m, &mg[u], &cl[u]);
+      } else {
+        al[u] = 1.f; mg[u] = 0.f; cl[u] = 0.f;
+      }
+    }
+    st4(alpha + ro + k, make_float4(al[0], al[1], al[2], al[3]));
+    if (a.two_d) {
+      st4(Mg + ro + k, make_float4(mg[0], mg[1], mg[2], mg[3]));
+      st4(clean + ro + k, make_float4(cl[0], cl[1], cl[2], cl[3]));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -332,7 +363,7 @@ __device__ __forceinline__ float spreading_gain(float dz, float level_db) {
   const float s_offset = (25.0f - s_up) / 2.0f;
   const float y = dz + 0.474f;
   const float sf_db = 15.81f + (s_offset * y) - (s_total * sqrtf(1.0f + (y * y)));
-  return powf(10.0f, sf_db / 10.0f);
+  return exp10f(sf_db / 10.0f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -352,21 +383,63 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
     const int kend = g.task_band[task + 1 < g.ntask ? task + 1 : task] == b && task + 1 < g.ntask
                          ? g.task_k[task + 1] : g.band_start[b + 1];
     float e0 = 0.f, l0 = 0.f, v0 = 0.f, e1 = 0.f, l1 = 0.f, v1 = 0.f;
-    for (int k = k0 + lane; k < kend; k += 32) {
-      const float s = stable[ro + k];
-      const float sv = fmaxf(s, kSpectralEps);
-      e0 += s; v0 += sv; l0 += log10f(sv);
-      if (two_d) {
-        const float fu = fmaxf(Xre_t[ro + k] - noise_t[ro + k], 0.0f);   // masking_veto.c:151-157
-        const float fv = fmaxf(fu, kSpectralEps);
-        e1 += fu; v1 += fv; l1 += log10f(fv);
+    // a task is at most 128 bins in all but extreme geometries: its (up to) 4 loads per lane
+    // and row are requested together, then summed in the same k order as a plain loop
+    for (int kb = k0 + lane; kb < kend; kb += 128) {
+      float sl[4], xr[4], nz[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = kb + 32 * u;
+        const bool in = k < kend;
+        sl[u] = in ? stable[ro + k] : 0.f;
+        xr[u] = (in && two_d) ? Xre_t[ro + k] : 0.f;
+        nz[u] = (in && two_d) ? noise_t[ro + k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (kb + 32 * u < kend) {
+          const float s = sl[u];
+          const float sv = fmaxf(s, kSpectralEps);
+          e0 += s; v0 += sv; l0 += log10f(sv);
+          if (two_d) {
+            const float fu = fmaxf(xr[u] - nz[u], 0.0f);   // masking_veto.c:151-157
+            const float fv = fmaxf(fu, kSpectralEps);
+            e1 += fu; v1 += fv; l1 += log10f(fv);
+          }
+        }
       }
     }
-    e0 = warp_sum(e0); l0 = warp_sum(l0); v0 = warp_sum(v0);
-    if (two_d) { e1 = warp_sum(e1); l1 = warp_sum(l1); v1 = warp_sum(v1); }
-    if (lane == 0) {
-      PART[0][task] = e0; PART[1][task] = l0; PART[2][task] = v0;
-      PART[3][task] = e1; PART[4][task] = l1; PART[5][task] = v1;
+    // the six sums in one transposing butterfly (9 shuffles instead of 30): at xor 16 / 8 / 4 a
+    // lane keeps the half of its values that its own bit selects and hands over the other
+    // half, then xor 2 / 1 finish the one value left.  Same pairing as warp_sum, same bits.
+    float v8[8] = {e0, l0, v0, e1, l1, v1, 0.f, 0.f};
+    {
+      const bool h = lane & 16;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float keep = h ? v8[q + 4] : v8[q], give = h ? v8[q] : v8[q + 4];
+        v8[q] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+    }
+    {
+      const bool h = lane & 8;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const float keep = h ? v8[q + 2] : v8[q], give = h ? v8[q] : v8[q + 2];
+        v8[q] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+      }
+    }
+    {
+      const bool h = lane & 4;
+      const float keep = h ? v8[1] : v8[0], give = h ? v8[0] : v8[1];
+      v8[0] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    }
+    v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
+    v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
+    // lane 4 * idx holds sum idx, idx = 4 * bit4 + 2 * bit3 + bit2
+    if ((lane & 3) == 0) {
+      const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      if (idx < 6) PART[idx][task] = v8[0];
     }
   }
   __syncthreads();
@@ -387,10 +460,12 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
   }
   __syncthreads();
   // spreading terms (E_j g(i-j, L_j))^0.4 for every (spectrum, band i, band j): all threads
-  for (int item = threadIdx.x; item < nspec * g.nb * g.nb; item += blockDim.x) {
-    const int s = item / (g.nb * g.nb);
-    const int r = item - s * (g.nb * g.nb);
-    const int b = r / g.nb, j = r - b * g.nb;
+  const int nb2 = g.nb * g.nb;
+  const unsigned nbmagic = (65536u + (unsigned)g.nb - 1u) / (unsigned)g.nb;   // r / nb for r < 1024, nb <= 32
+  for (int item = threadIdx.x; item < nspec * nb2; item += blockDim.x) {
+    const int s = item >= nb2 ? 1 : 0;
+    const int r = item - s * nb2;
+    const int b = (int)(((unsigned)r * nbmagic) >> 16), j = r - b * g.nb;
     const float dz = (float)b - (float)j;
     const float gain = spreading_gain(dz, LV[s][j]);
     TERM[s][b][j] = powf(E[s][j] * gain, kAdditivityExp);
@@ -452,9 +527,23 @@ nmr_kernel(const GeoK g, int first_active, const float* __restrict__ band_T,
                          ? g.task_k[task + 1] : g.band_start[b + 1];
     const float spl = SPLs[b], vT = VT[b];
     float sn = 0.f, sth = 0.f;
-    for (int k = k0 + lane; k < kend; k += 32) {
-      sn += noise_t[ro + k];
-      sth += (spl >= __ldg(&g.abs_thr_spl[k])) ? vT : __ldg(&g.abs_thr_lin[k]);
+    for (int kb = k0 + lane; kb < kend; kb += 128) {   // loads batched as in band_kernel
+      float nz[4], ts[4], tl[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = kb + 32 * u;
+        const bool in = k < kend;
+        nz[u] = in ? noise_t[ro + k] : 0.f;
+        ts[u] = in ? __ldg(&g.abs_thr_spl[k]) : 0.f;
+        tl[u] = in ? __ldg(&g.abs_thr_lin[k]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (kb + 32 * u < kend) {
+          sn += nz[u];
+          sth += (spl >= ts[u]) ? vT : tl[u];
+        }
+      }
     }
     sn = warp_sum(sn);
     sth = warp_sum(sth);
@@ -666,7 +755,44 @@ struct FinalArgs {
   float depth, reduction, tonal, whitening;
 };
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float final_gain(const GeoK& g, const FinalArgs& a, const float* prot, int k,
+                                            float n, float spec, float al, float stab, float mroot,
+                                            float wtv) {
+  if (a.use_veto) {
+    // masking_veto.c:230-266
+    // bp = lerp(prot[cb], prot[cb + 1], t); t (sb_geometry.cu) is 0 where the reference takes
+    // prot[cb] alone, and prot[] is 0 past the last band, so the one expression covers all cases
+    const int cb = __ldg(&g.cband[k]);
+    const float tc = __ldg(&g.veto_t[k]);
+    const float y0 = prot[cb], y1 = prot[cb + 1];
+    const float bp = (y0 * (1.0f - tc)) + (y1 * tc);
+    const float bin_snr = stab / (n + kSpectralEps);
+    const float sc = fminf(bin_snr / 1.0f, 1.0f);
+    const float veto = bp * sc * a.depth;
+    al = al + ((1.0f - al) * veto);
+  }
+  // gain_calculator.c:27-69
+  const float sn = n * al;
+  float gain;
+  if (sn > FLT_MIN) gain = (spec > sn) ? (spec - sn) / spec : 0.0f;
+  else gain = 1.0f;
+  // noise_floor_manager.c:94-157
+  if (a.reduction >= 0.999f && a.tonal >= 0.999f) {
+    gain = 1.0f;
+  } else {
+    const float m = mroot;           // mask^(1/4), taken by the caller
+    const float dual = (a.reduction * (1.0f - m)) + (a.tonal * m);
+    const float target = dual + (a.whitening * (a.reduction - dual));
+    const float rdepth = 1.0f - target;
+    const float eff = 1.0f + (rdepth * (wtv - 1.0f));
+    float fl = target * eff;
+    if (fl > 1.0f) fl = 1.0f;
+    gain = fmaxf(fl, gain);
+  }
+  return gain;
+}
+
+__global__ void __launch_bounds__(512)
 final_kernel(const GeoK g, FinalArgs a, const float* __restrict__ Xre_t,
              const float* __restrict__ Xim_t, const float* __restrict__ noise_t,
              const float* __restrict__ Mg, const float* __restrict__ alpha,
@@ -674,7 +800,7 @@ final_kernel(const GeoK g, FinalArgs a, const float* __restrict__ Xre_t,
              const float* __restrict__ wt, const float* __restrict__ mask,
              float* __restrict__ Yre, float* __restrict__ Yim) {
   __shared__ float prot[kBandPitch];
-  const int i = blockIdx.y;
+  const int i = blockIdx.x;
   const bool active = i >= a.first_active;
   if (active && a.use_veto) {
     if (threadIdx.x < kBandPitch) {
@@ -694,70 +820,66 @@ final_kernel(const GeoK g, FinalArgs a, const float* __restrict__ Xre_t,
     }
     __syncthreads();
   }
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= g.Kp) return;
-  const size_t o = (size_t)i * g.Kp + k;
-  const float xr = Xre_t[o], xi = Xim_t[o];
-  if (!active || k >= g.K) {
-    Yre[o] = xr;
-    Yim[o] = xi;
-    return;
-  }
-  const float n = noise_t[o];
-  const float spec = Mg[o];
-  float al = alpha[o];
-  if (a.use_veto) {
-    // masking_veto.c:230-266
-    const int cb = __ldg(&g.cband[k]);
-    float bp;
-    if (cb < g.nb - 1) {
-      const float x0 = g.centre[cb], x1 = g.centre[cb + 1];
-      const float y0 = prot[cb], y1 = prot[cb + 1];
-      if (x1 > x0) {
-        const float t = ((float)k - x0) / (x1 - x0);
-        const float tc = fmaxf(0.0f, fminf(1.0f, t));
-        bp = (y0 * (1.0f - tc)) + (y1 * tc);
-      } else {
-        bp = y0;
-      }
-    } else {
-      bp = prot[g.nb - 1];
+  const size_t ro = (size_t)i * g.Kp;
+  const bool floor_on = !(a.reduction >= 0.999f && a.tonal >= 0.999f);
+  const float* __restrict__ mrow = mask + (size_t)i * a.mask_stride;
+  const float* __restrict__ wrow = wt + (size_t)i * a.wt_stride;
+  for (int k = 4 * threadIdx.x; k < g.Kp; k += 4 * blockDim.x) {
+    const float4 xr4 = ld4(Xre_t + ro + k), xi4 = ld4(Xim_t + ro + k);
+    if (!active) {
+      st4(Yre + ro + k, xr4);
+      st4(Yim + ro + k, xi4);
+      continue;
     }
-    const float bin_snr = stable[o] / (n + kSpectralEps);
-    const float sc = fminf(bin_snr / 1.0f, 1.0f);
-    const float veto = bp * sc * a.depth;
-    al = al + ((1.0f - al) * veto);
-  }
-  // gain_calculator.c:27-69
-  const float sn = n * al;
-  float gain;
-  if (sn > FLT_MIN) gain = (spec > sn) ? (spec - sn) / spec : 0.0f;
-  else gain = 1.0f;
-  // noise_floor_manager.c:94-157
-  if (a.reduction >= 0.999f && a.tonal >= 0.999f) {
-    gain = 1.0f;
-  } else {
-    float m = mask[(size_t)i * a.mask_stride + k];
-    if (m > 0.0f) m = sqrtf(sqrtf(m));
-    const float dual = (a.reduction * (1.0f - m)) + (a.tonal * m);
-    const float target = dual + (a.whitening * (a.reduction - dual));
-    const float rdepth = 1.0f - target;
-    const float eff = 1.0f + (rdepth * (wt[(size_t)i * a.wt_stride + k] - 1.0f));
-    float fl = target * eff;
-    if (fl > 1.0f) fl = 1.0f;
-    gain = fmaxf(fl, gain);
-  }
-  // denoiser_post_process.c:36-50
-  if (a.residual) {
-    Yre[o] = xr - (xr * gain);
-    Yim[o] = xi - (xi * gain);
-  } else {
-    Yre[o] = xr * gain;
-    Yim[o] = xi * gain;
+    const float4 n4 = ld4(noise_t + ro + k), sp4 = ld4(Mg + ro + k), al4 = ld4(alpha + ro + k);
+    float4 sb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.use_veto) sb4 = ld4(stable + ro + k);
+    const float xr[4] = {xr4.x, xr4.y, xr4.z, xr4.w}, xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+    const float nv[4] = {n4.x, n4.y, n4.z, n4.w}, sp[4] = {sp4.x, sp4.y, sp4.z, sp4.w};
+    const float al[4] = {al4.x, al4.y, al4.z, al4.w}, sb[4] = {sb4.x, sb4.y, sb4.z, sb4.w};
+    float yr[4], yi[4], mq[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) mq[u] = (floor_on && k + u < g.K) ? mrow[k + u] : 0.f;
+    // noise_floor_manager.c:129-131: mask^(1/4); the tonal mask is zero almost everywhere, the
+    // two square roots are skipped for a whole group of bins without a tonal component
+    if (mq[0] > 0.0f || mq[1] > 0.0f || mq[2] > 0.0f || mq[3] > 0.0f) {
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (mq[u] > 0.0f) mq[u] = sqrtf(sqrtf(mq[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k + u < g.K) {
+        const float wtv = floor_on ? wrow[k + u] : 1.f;
+        const float gain = final_gain(g, a, prot, k + u, nv[u], sp[u], al[u], sb[u], mq[u], wtv);
+        // denoiser_post_process.c:36-50
+        if (a.residual) {
+          yr[u] = xr[u] - (xr[u] * gain);
+          yi[u] = xi[u] - (xi[u] * gain);
+        } else {
+          yr[u] = xr[u] * gain;
+          yi[u] = xi[u] * gain;
+        }
+      } else {
+        yr[u] = xr[u];
+        yi[u] = xi[u];
+      }
+    }
+    st4(Yre + ro + k, make_float4(yr[0], yr[1], yr[2], yr[3]));
+    st4(Yim + ro + k, make_float4(yi[0], yi[1], yi[2], yi[3]));
   }
 }
 
 }  // namespace
+
+// CTA size of the one-row-per-CTA elementwise kernels: the row's quads over the fewest rounds
+// of at most 512 threads, rounded up to a warp
+static int row_threads(const GeoK& g) {
+  const int quads = g.Kp / 4;
+  const int rounds = (quads + 511) / 512;
+  const int t = (quads + rounds - 1) / rounds;
+  return ((t + 31) / 32) * 32;
+}
 
 bool launch_morph_profile(const GeoK& g, const float* prof, float aggressiveness, float* out,
                           cudaStream_t st) {
@@ -780,8 +902,7 @@ bool launch_snr(const GeoK& g, const float* P, const float* noise, float* S, int
                 cudaStream_t st) {
   KTimer kt_(kcSnr, st);
   if (frames <= 0) return true;
-  dim3 grid((g.Kp + 255) / 256, frames);
-  snr_kernel<<<grid, 256, 0, st>>>(g, P, noise, S);
+  snr_kernel<<<frames, row_threads(g), 0, st>>>(g, P, noise, S);
   SB_LAUNCH_CHECK();
   return true;
 }
@@ -833,10 +954,9 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
     pa.mask_stride = a.mask_stride;
     pa.alpha_max_user = kAlphaMin + (a.strength * (kAlphaMax - kAlphaMin));
     pa.tonal_gain = a.tonal;
-    dim3 grid((g.Kp + 255) / 256, active);
     {
       KTimer kt_(kcGainPre, st);
-    gain_pre_kernel<<<grid, 256, 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, a.mask, L.Mg,
+    gain_pre_kernel<<<active, row_threads(g), 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, a.mask, L.Mg,
                                           L.alpha, L.stable);
     SB_LAUNCH_CHECK();
     }
@@ -898,10 +1018,9 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
   fa2.reduction = a.reduction;
   fa2.tonal = a.tonal;
   fa2.whitening = a.whitening;
-  dim3 grid((g.Kp + 255) / 256, M);
   {
     KTimer kt_(kcFinal, st);
-  final_kernel<<<grid, 256, 0, st>>>(g, fa2, L.Xre, L.Xim, L.noise, L.Mg, L.alpha, L.stable,
+  final_kernel<<<M, row_threads(g), 0, st>>>(g, fa2, L.Xre, L.Xim, L.noise, L.Mg, L.alpha, L.stable,
                                      L.band_p, a.wt, a.mask, L.Yre, L.Yim);
   SB_LAUNCH_CHECK();
   }

@@ -278,6 +278,19 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
     for (int b = 0; b < g.nb; b++)
       for (int k = g.band_start[b]; k < g.band_start[b + 1]; k++) bob[k] = b;
   }
+  // masking_veto.c:238-250: the interpolation weight of a bin depends on the geometry only.
+  // 0 where the reference takes the lower band alone (last band, coincident centres).
+  std::vector<float> veto_t(g.Kp, 0.f);
+  for (int k = 0; k < g.K; k++) {
+    const int cb = cband[k];
+    if (cb < g.nb - 1) {
+      const float x0 = g.centre[cb], x1 = g.centre[cb + 1];
+      if (x1 > x0) {
+        const float t = ((float)k - x0) / (x1 - x0);
+        veto_t[k] = fmaxf(0.0f, fminf(1.0f, t));
+      }
+    }
+  }
 
   g.win = upload(G, win);
   g.tw = upload(G, tw);
@@ -286,9 +299,10 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
   g.abs_thr_spl = upload(G, thr_spl);
   g.abs_thr_lin = upload(G, thr_lin);
   g.cband = upload(G, cband);
+  g.veto_t = upload(G, veto_t);
   g.band_of_bin = upload(G, bob);
   if (!g.win || !g.tw || !g.twn || !g.twg || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
-      !g.band_of_bin) {
+      !g.veto_t || !g.band_of_bin) {
     set_error("geometry upload", cudaGetLastError(), __FILE__, __LINE__);
     for (void* p : G->dev_allocs) cudaFree(p);
     delete G;
