@@ -230,96 +230,143 @@ nlm_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_
 
 // ---------------------------------------------------------------------------
 // Tail kernel: the partial paste block [8*nfull, K) with clamped centre K-1.
-// One CTA per target, one thread per (dt, df) candidate, then bins are pasted
-// by `lim` threads walking the 357 weights in the reference's flat order.
+// A warp per target (8 consecutive targets per CTA over one staged window), lanes over
+// the distinct (dt, clamped centre) candidates, then the bins are pasted in the
+// reference's flat (dt, df) order with the running sums chained through shuffles.
 // ---------------------------------------------------------------------------
+constexpr int TAILT = 8;     // targets (warps) per CTA
 constexpr int TAILW = 32;    // staged columns: bins bc-12 .. bc+19 (clamped)
 
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(TAILT * 32)
 nlm_tail_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
-                float h, float* __restrict__ out, int pitchO) {
-  __shared__ float tile[NDT][TAILW + 1];
-  __shared__ float wgt[NDT * 17];
-  const int target = blockIdx.x;
-  const int row_t = first_target_row + target;
+                int targets, float h, float* __restrict__ out, int pitchO) {
+  // A warp per target, TAILT consecutive targets per CTA over one staged window of
+  // TAILT + 20 frames; the target's own 8x8 patch stays in registers, lanes take the
+  // candidates.
+  __shared__ float tile[TAILT + NDT - 1][TAILW + 1];
+  __shared__ float wgt[TAILT][NDT * 17];
+  __shared__ float live_w[TAILT][NDT * 17];
+  __shared__ unsigned short live_idx[TAILT][NDT * 17];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tau0 = blockIdx.x * TAILT;
+  const int nt = targets - tau0 < TAILT ? targets - tau0 : TAILT;      // targets of this CTA
+  const int row0 = first_target_row + tau0 - kNlmPast;                 // frame of tile row 0
   const int bs = 8 * nfull;
   const int lim = K - bs;
   int bc = bs + 4;
   if (bc >= K) bc = K - 1;
   const int c_origin = bc - 12;
-  for (int e = threadIdx.x; e < NDT * TAILW; e += blockDim.x) {
+  for (int e = threadIdx.x; e < (nt + NDT - 1) * TAILW; e += blockDim.x) {
     const int r = e / TAILW, c_rel = e - r * TAILW;
     int c = c_origin + c_rel;
     c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
-    tile[r][c_rel] = S[(size_t)(row_t - kNlmPast + r) * pitchS + c];
+    tile[r][c_rel] = S[(size_t)(row0 + r) * pitchS + c];
   }
   __syncthreads();
+  if (warp >= nt) return;
+  const int target = tau0 + warp;
+  const float (*tw)[TAILW + 1] = &tile[warp];     // tw[r]: frame t - 16 + r of this target
   float tsum = 0.0f;
-  for (int i = 0; i < lim; i++) tsum += tile[kNlmPast][bs + i - c_origin];
+  for (int i = 0; i < lim; i++) tsum += tw[kNlmPast][bs + i - c_origin];
   const bool live = tsum >= 1e-6f;
   float inv, thr;
   block_params(bc, K, h, &inv, &thr);
-  if (threadIdx.x < NDT * 17) {
-    float w = 0.0f;
-    if (live) {
-      const int dti = threadIdx.x / 17;
-      const int df = threadIdx.x - dti * 17 - kNlmRangeFreq;
+  // Candidates whose clamped centre cc coincides have the same patch, hence the same distance
+  // and weight: with the block centre on (or next to) the last bin, df >= K-1-bc all clamp to
+  // K-1 (9 of the 17 df when K = 8 nfull + 1).  One evaluation per DISTINCT (dt, cc).
+  const int cc_min = bc - kNlmRangeFreq < 0 ? 0 : bc - kNlmRangeFreq;
+  const int cc_max = bc + kNlmRangeFreq > K - 1 ? K - 1 : bc + kNlmRangeFreq;
+  const int ncc = cc_max - cc_min + 1;
+  float* wg = wgt[warp];
+  if (live) {
+    float tp[8][8];                                // the target patch, element-wise clamped
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int q = 0; q < 8; q++) tp[r][q] = tw[kNlmPast - 4 + r][bc - 4 + q - c_origin];
+    int dti = 0, ci = lane;
+    while (ci >= ncc) { ci -= ncc; dti++; }
+    while (dti < NDT) {
       const int dt = dti - kNlmPast;
-      int cc = bc + df;
-      cc = cc < 0 ? 0 : (cc > K - 1 ? K - 1 : cc);
+      const int cc = cc_min + ci;
       float a[8];
 #pragma unroll
       for (int q = 0; q < 8; q++) a[q] = 0.0f;
 #pragma unroll
       for (int r = 0; r < 8; r++) {
-        const float* tr = tile[kNlmPast - 4 + r];
-        const float* cr = tile[ring_row(dt + r - 4)];
+        const float* cr = tw[ring_row(dt + r - 4)] + (cc - 4 - c_origin);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          const float d = tr[bc - 4 + q - c_origin] - cr[cc - 4 + q - c_origin];
+          const float d = tp[r][q] - cr[q];
           a[q] = fmaf(d, d, a[q]);
         }
       }
       const float d = hsum8(a);
+      float w = 0.0f;
       if (!(d > thr)) {
         w = schraudolph_exp(-d * inv);
         if (w < kNlmMinWeight) w = 0.0f;
       }
+      wg[dti * 17 + ci] = w;
+      ci += 32;
+      while (ci >= ncc) { ci -= ncc; dti++; }
     }
-    wgt[threadIdx.x] = w;
   }
-  __syncthreads();
+  __syncwarp();
   // compact the (few) non-zero weights, keeping the reference's flat (dt, df) order
-  __shared__ unsigned short live_idx[NDT * 17];
-  __shared__ int n_live;
-  if (threadIdx.x < 32) {
-    int base = 0;
+  int n_live = 0;
+  if (live) {
     for (int c0 = 0; c0 < NDT * 17; c0 += 32) {
-      const int c = c0 + threadIdx.x;
-      const bool on = c < NDT * 17 && wgt[c] > 0.0f;
+      const int c = c0 + lane;
+      float w = 0.0f;
+      if (c < NDT * 17) {
+        const int dti = c / 17;
+        int cc = bc + (c - dti * 17) - kNlmRangeFreq;
+        cc = cc < cc_min ? cc_min : (cc > cc_max ? cc_max : cc);
+        w = wg[dti * 17 + cc - cc_min];
+      }
+      const bool on = w > 0.0f;
       const unsigned m = __ballot_sync(0xffffffffu, on);
-      if (on) live_idx[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned short)c;
-      base += __popc(m);
+      if (on) {
+        const int pos = n_live + __popc(m & ((1u << lane) - 1u));
+        live_idx[warp][pos] = (unsigned short)c;
+        live_w[warp][pos] = w;
+      }
+      n_live += __popc(m);
     }
-    if (threadIdx.x == 0) n_live = base;
   }
-  __syncthreads();
-  if (threadIdx.x < lim) {
-    const int i = threadIdx.x;
+  __syncwarp();
+  // Paste in the reference's order.  In this top-frequency block most candidates pass
+  // (thr grows with (1 + 3 f^2)^2), so a lane walking the list alone spent its time in the
+  // load -> FMA latency chain: the lanes fetch 32 (weight, value) pairs at once and the sums
+  // are chained through shuffles (every lane carries the same running sums).
+  for (int i = 0; i < lim; i++) {
     float acc = 0.0f, ws = 0.0f;
-    const int n = n_live;
-    for (int e = 0; e < n; e++) {
-      const int c = live_idx[e];
-      const int dti = c / 17;
-      const int dfi = c - dti * 17;
-      const float w = wgt[c];
-      int cb = bs + i + dfi - kNlmRangeFreq;
-      cb = cb < 0 ? 0 : (cb > K - 1 ? K - 1 : cb);
-      acc = fmaf(w, tile[dti][cb - c_origin], acc);   // frame t+dt, dt = dti-16, never wraps
-      ws += w;
+    for (int e0 = 0; e0 < n_live; e0 += 32) {
+      const int e = e0 + lane;
+      float w = 0.0f, v = 0.0f;
+      if (e < n_live) {
+        const int c = live_idx[warp][e];
+        const int dti = c / 17;
+        const int dfi = c - dti * 17;
+        w = live_w[warp][e];
+        int cb = bs + i + dfi - kNlmRangeFreq;
+        cb = cb < 0 ? 0 : (cb > K - 1 ? K - 1 : cb);
+        v = tw[dti][cb - c_origin];                 // frame t+dt, dt = dti-16, never wraps
+      }
+      const int cnt = n_live - e0 < 32 ? n_live - e0 : 32;
+#pragma unroll 8
+      for (int j = 0; j < cnt; j++) {
+        const float wj = __shfl_sync(0xffffffffu, w, j);
+        const float vj = __shfl_sync(0xffffffffu, v, j);
+        acc = fmaf(wj, vj, acc);
+        ws += wj;
+      }
     }
-    const float tv = tile[kNlmPast][bs + i - c_origin];
-    out[(size_t)target * pitchO + bs + i] = (ws > kNlmMinWeight) ? acc / ws : tv;
+    if (lane == 0) {
+      const float tv = tw[kNlmPast][bs + i - c_origin];
+      out[(size_t)target * pitchO + bs + i] = (ws > kNlmMinWeight) ? acc / ws : tv;
+    }
   }
 }
 
@@ -721,7 +768,8 @@ bool launch_nlm(const GeoK& g, const float* S, int first_target_row, int targets
   delete kt;
   if (g.K % 8 != 0) {
     KTimer kt2(kcNlmTail, st);
-    nlm_tail_kernel<<<targets, 384, 0, st>>>(S, g.Kp, g.K, nfull, first_target_row, h, Shat, g.Kp);
+    nlm_tail_kernel<<<(targets + TAILT - 1) / TAILT, TAILT * 32, 0, st>>>(S, g.Kp, g.K, nfull, first_target_row,
+                                                                          targets, h, Shat, g.Kp);
     SB_LAUNCH_CHECK();
   }
   return true;
