@@ -651,12 +651,35 @@ rowscan_kernel(int ncols, int pitch, int rows, const float* A, float* B,   // B 
     if (warp == 0) {
       const int nr = (rows - t * kRsTile < kRsTile) ? rows - t * kRsTile : kRsTile;
       float* tp = &ring[t % kRsRing][0][lane];
-#pragma unroll 8
-      for (int r = 0; r < nr; r++) {
-        const float v = tp[r * 32];
-        if (MODE == 0) m = (kVetoSmoothing * v) + ((1.0f - kVetoSmoothing) * m);
-        else m = fmaf(c, m, v);
-        tp[r * 32] = m;
+      // One dependent FFMA per frame is the floor of this loop.  MODE 0: both products of
+      // 0.5 v + 0.5 m are exact, so fma(0.5, m, 0.5 v) rounds to the same value and keeps the
+      // multiply of v off the chain.  Full tiles are unrolled in groups of 16 frames whose
+      // loads are issued before the chain needs them.  (Measured: the scanner warp and the
+      // movers each need ~10 cycles per frame, the barrier ~300 per tile; a deeper ring
+      // (12 tiles, 10 ahead), 4 / 8 / 16 mover warps or unrolled movers changed nothing.)
+      if (nr == kRsTile) {
+#pragma unroll
+        for (int r0 = 0; r0 < kRsTile; r0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; u++) {
+            v[u] = tp[(r0 + u) * 32];
+            if (MODE == 0) v[u] *= kVetoSmoothing;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; u++) {
+            if (MODE == 0) m = fmaf(1.0f - kVetoSmoothing, m, v[u]);
+            else m = fmaf(c, m, v[u]);
+            tp[(r0 + u) * 32] = m;
+          }
+        }
+      } else {
+        for (int r = 0; r < nr; r++) {
+          const float v = tp[r * 32];
+          if (MODE == 0) m = fmaf(1.0f - kVetoSmoothing, m, kVetoSmoothing * v);
+          else m = fmaf(c, m, v);
+          tp[r * 32] = m;
+        }
       }
     } else if (t > 0) {
       store_tile(t - 1);                     // finished in the previous iteration

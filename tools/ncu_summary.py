@@ -42,7 +42,9 @@ def src(path, top=14):
     ops, thr, smp = collections.Counter(), collections.Counter(), collections.Counter()
     tot = 0
     for r in rows[2:]:
-        if len(r) <= iI:
+        if r and r[0] == "Kernel Name":
+            break                                 # export holds several kernels: first one only
+        if len(r) <= iI or not r[iI].strip().isdigit():
             continue
         parts = r[iS].split()
         op = parts[1] if parts[0].startswith("@") else parts[0]
