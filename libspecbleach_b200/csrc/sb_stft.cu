@@ -232,11 +232,38 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
 
 // ---------------------------------------------------------------------------
 // forward: frame f = xbuf[f*hop, f*hop+frame) -> Hann -> centre in N -> rFFT
+//
+// VEC (geometries with cp % 4 == 0, frame % 4 == 0, hop even, M % 4 == 0 -- 48 kHz / 50 ms,
+// 96 kHz / 77 ms ...): sample pairs (forward) and bin / sample quads (inverse) move as 64 /
+// 128-bit accesses.  Same arithmetic per element in both forms.
 // ---------------------------------------------------------------------------
+// one bin of the real spectrum from the packed transform Z (k in [0, Kp))
+__device__ __forceinline__ void split_bin(const float2* Z, int M, const float2* __restrict__ twn, int k,
+                                          float* xr_out, float* xi_out) {
+  float xr = 0.f, xi = 0.f;
+  if (k == 0) {
+    xr = Z[0].x + Z[0].y;
+  } else if (k == M) {
+    xr = Z[0].x - Z[0].y;
+  } else if (k < M) {
+    const float2 z1 = Z[k];
+    const float2 z2 = Z[M - k];
+    const float er = 0.5f * (z1.x + z2.x), ei = 0.5f * (z1.y - z2.y);
+    const float dr = 0.5f * (z1.x - z2.x), di = 0.5f * (z1.y + z2.y);
+    // O = D / i = (di, -dr);  X = E + w_N^k * O
+    const float2 w = __ldg(&twn[k]);
+    xr = er + (di * w.x + dr * w.y);
+    xi = ei + (di * w.y - dr * w.x);
+  }
+  *xr_out = xr;
+  *xi_out = xi;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(kFftMaxThreads)
 forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__ Xre,
                float* __restrict__ Xim, float* __restrict__ P) {
-  extern __shared__ float2 smem[];
+  extern __shared__ __align__(16) float2 smem[];
   float2* a = smem;
   float2* b = smem + g.M;
   const int f = blockIdx.x;
@@ -250,9 +277,19 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int i0 = 2 * (k0 + u * (int)blockDim.x) - g.cp;
-      const int i1 = i0 + 1;
-      v0[u] = (i0 >= 0 && i0 < g.frame) ? src[i0] * __ldg(&win[i0]) : 0.f;
-      v1[u] = (i1 >= 0 && i1 < g.frame) ? src[i1] * __ldg(&win[i1]) : 0.f;
+      if (VEC) {   // i0 even, frame even: the pair is inside the frame or outside it as a whole
+        float2 sv = make_float2(0.f, 0.f), wv = make_float2(0.f, 0.f);
+        if (i0 >= 0 && i0 < g.frame) {
+          sv = *reinterpret_cast<const float2*>(src + i0);
+          wv = __ldg(reinterpret_cast<const float2*>(win + i0));
+        }
+        v0[u] = sv.x * wv.x;
+        v1[u] = sv.y * wv.y;
+      } else {
+        const int i1 = i0 + 1;
+        v0[u] = (i0 >= 0 && i0 < g.frame) ? src[i0] * __ldg(&win[i0]) : 0.f;
+        v1[u] = (i1 >= 0 && i1 < g.frame) ? src[i1] * __ldg(&win[i1]) : 0.f;
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -267,22 +304,11 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
   float* __restrict__ im = Xim + (size_t)f * g.Kp;
   float* __restrict__ pw = P + (size_t)f * g.Kp;
   const int M = g.M;
+  // (one bin per thread also in the VEC form: four consecutive bins per thread put the Z
+  // reads 32 B apart, an 8-way bank conflict that cost more than the 128-bit stores saved)
   for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
-    float xr = 0.f, xi = 0.f;
-    if (k == 0) {
-      xr = Z[0].x + Z[0].y;
-    } else if (k == M) {
-      xr = Z[0].x - Z[0].y;
-    } else if (k < M) {
-      const float2 z1 = Z[k];
-      const float2 z2 = Z[M - k];
-      const float er = 0.5f * (z1.x + z2.x), ei = 0.5f * (z1.y - z2.y);
-      const float dr = 0.5f * (z1.x - z2.x), di = 0.5f * (z1.y + z2.y);
-      // O = D / i = (di, -dr);  X = E + w_N^k * O
-      const float2 w = __ldg(&g.twn[k]);
-      xr = er + (di * w.x + dr * w.y);
-      xi = ei + (di * w.y - dr * w.x);
-    }
+    float xr, xi;
+    split_bin(Z, M, g.twn, k, &xr, &xi);
     re[k] = xr;
     im[k] = xi;
     // spectral_features.c:80-107 (DC and Nyquist have xi == 0 exactly)
@@ -293,38 +319,80 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
 // ---------------------------------------------------------------------------
 // inverse: Y -> unnormalised HC2R -> OUTPUT window / scale -> centre crop
 // ---------------------------------------------------------------------------
+// packed input point k of the inverse transform from bins k and M - k
+__device__ __forceinline__ float2 merge_bins(float xr, float xi, float yr, float yi, float2 w) {
+  const float er = xr + yr, ei = xi + yi;
+  const float dr = xr - yr, di = xi - yi;
+  // t = conj(w) * D ; Z = E + i*t
+  const float tr = dr * w.x + di * w.y;
+  const float ti = di * w.x - dr * w.y;
+  return make_float2(er - ti, ei + tr);
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(kFftMaxThreads)
 inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restrict__ Yim,
                float* __restrict__ synth) {
-  extern __shared__ float2 smem[];
+  extern __shared__ __align__(16) float2 smem[];
   float2* a = smem;
   float2* b = smem + g.M;
   const int f = blockIdx.x;
   const int M = g.M;
   const float* __restrict__ re = Yre + (size_t)f * g.Kp;
   const float* __restrict__ im = Yim + (size_t)f * g.Kp;
-  for (int k0 = threadIdx.x; k0 < M; k0 += 4 * blockDim.x) {   // loads batched as in forward_kernel
-    float xr[4], xi[4], yr[4], yi[4];
-    float2 w[4];
+  if (VEC) {
+    // quads of bins k .. k+3 (128-bit) against the mirrored bins M-k .. M-k-3 (scalar: they
+    // sit at odd offsets), two quads per thread requested before the first is used
+    for (int k0 = 4 * threadIdx.x; k0 < M; k0 += 8 * blockDim.x) {
+      float4 r4[2], i4[2], w01[2], w23[2];
+      float yr[2][4], yi[2][4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int k = k0 + u * (int)blockDim.x;
-      const bool in = k < M;
-      xr[u] = in ? re[k] : 0.f;
-      xi[u] = (in && k != 0) ? im[k] : 0.f;
-      yr[u] = in ? re[M - k] : 0.f;
-      yi[u] = (in && k != 0) ? -im[M - k] : 0.f;   // conj X[M-k]
-      w[u] = in ? __ldg(&g.twn[k]) : make_float2(0.f, 0.f);
+      for (int h = 0; h < 2; h++) {
+        const int k = k0 + 4 * h * (int)blockDim.x;
+        const bool in = k < M;
+        r4[h] = in ? *reinterpret_cast<const float4*>(re + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        i4[h] = in ? *reinterpret_cast<const float4*>(im + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w01[h] = in ? __ldg(reinterpret_cast<const float4*>(g.twn + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w23[h] = in ? __ldg(reinterpret_cast<const float4*>(g.twn + k + 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          yr[h][u] = in ? re[M - k - u] : 0.f;
+          yi[h][u] = (in && k + u != 0) ? -im[M - k - u] : 0.f;   // conj X[M-k]
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int k = k0 + 4 * h * (int)blockDim.x;
+        if (k < M) {
+          const float xi0 = (k == 0) ? 0.f : i4[h].x;
+          const float2 z0 = merge_bins(r4[h].x, xi0, yr[h][0], yi[h][0], make_float2(w01[h].x, w01[h].y));
+          const float2 z1 = merge_bins(r4[h].y, i4[h].y, yr[h][1], yi[h][1], make_float2(w01[h].z, w01[h].w));
+          const float2 z2 = merge_bins(r4[h].z, i4[h].z, yr[h][2], yi[h][2], make_float2(w23[h].x, w23[h].y));
+          const float2 z3 = merge_bins(r4[h].w, i4[h].w, yr[h][3], yi[h][3], make_float2(w23[h].z, w23[h].w));
+          *reinterpret_cast<float4*>(a + k) = make_float4(z0.x, z0.y, z1.x, z1.y);
+          *reinterpret_cast<float4*>(a + k + 2) = make_float4(z2.x, z2.y, z3.x, z3.y);
+        }
+      }
     }
+  } else {
+    for (int k0 = threadIdx.x; k0 < M; k0 += 4 * blockDim.x) {   // loads batched as in forward_kernel
+      float xr[4], xi[4], yr[4], yi[4];
+      float2 w[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int k = k0 + u * (int)blockDim.x;
-      const float er = xr[u] + yr[u], ei = xi[u] + yi[u];
-      const float dr = xr[u] - yr[u], di = xi[u] - yi[u];
-      // t = conj(w) * D ; Z = E + i*t
-      const float tr = dr * w[u].x + di * w[u].y;
-      const float ti = di * w[u].x - dr * w[u].y;
-      if (k < M) a[k] = make_float2(er - ti, ei + tr);
+      for (int u = 0; u < 4; u++) {
+        const int k = k0 + u * (int)blockDim.x;
+        const bool in = k < M;
+        xr[u] = in ? re[k] : 0.f;
+        xi[u] = (in && k != 0) ? im[k] : 0.f;
+        yr[u] = in ? re[M - k] : 0.f;
+        yi[u] = (in && k != 0) ? -im[M - k] : 0.f;   // conj X[M-k]
+        w[u] = in ? __ldg(&g.twn[k]) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = k0 + u * (int)blockDim.x;
+        if (k < M) a[k] = merge_bins(xr[u], xi[u], yr[u], yi[u], w[u]);
+      }
     }
   }
   __syncthreads();
@@ -336,12 +404,21 @@ inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restr
   // the quotient by the constant scale: reciprocal, one residual correction (the IEEE quotient
   // for every normal operand; the generic division sequence was 12 % of this kernel)
   const float scale = g.scale, inv_scale = 1.0f / scale;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < g.frame; i += blockDim.x) {
-    const float num = zf[g.cp + i] * __ldg(&win[i]);
+  auto quot = [&](float num) {
     const float q0 = num * inv_scale;
     const float rem = fmaf(-q0, scale, num);
-    out[i] = fmaf(rem, inv_scale, q0);
+    return fmaf(rem, inv_scale, q0);
+  };
+  if (VEC) {
+    for (int i = 4 * threadIdx.x; i < g.frame; i += 4 * blockDim.x) {
+      const float4 v = *reinterpret_cast<const float4*>(zf + g.cp + i);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(win + i));
+      *reinterpret_cast<float4*>(out + i) =
+          make_float4(quot(v.x * w.x), quot(v.y * w.y), quot(v.z * w.z), quot(v.w * w.w));
+    }
+  } else {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < g.frame; i += blockDim.x) out[i] = quot(zf[g.cp + i] * __ldg(&win[i]));
   }
 }
 
@@ -378,6 +455,11 @@ __global__ void ola_kernel(const GeoK g, const float* __restrict__ synth, int fr
 
 }  // namespace
 
+// geometries whose frame / padding / hop let the FFT kernels move pairs and quads (see forward_kernel)
+static bool fft_vec_ok(const GeoK& g) {
+  return g.cp % 4 == 0 && g.frame % 4 == 0 && g.hop % 2 == 0 && g.M % 4 == 0;
+}
+
 static bool set_fft_smem(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
     SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -390,8 +472,13 @@ bool launch_forward(const GeoK& g, const float* xbuf, int frames, float* Xre, fl
   KTimer kt_(kcForward, st);
   if (frames <= 0) return true;
   const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
-  if (!set_fft_smem((const void*)forward_kernel, smem)) return false;
-  forward_kernel<<<frames, g.fft_threads, smem, st>>>(g, xbuf, Xre, Xim, P);
+  if (fft_vec_ok(g) && ((uintptr_t)xbuf & 7) == 0) {
+    if (!set_fft_smem((const void*)forward_kernel<true>, smem)) return false;
+    forward_kernel<true><<<frames, g.fft_threads, smem, st>>>(g, xbuf, Xre, Xim, P);
+  } else {
+    if (!set_fft_smem((const void*)forward_kernel<false>, smem)) return false;
+    forward_kernel<false><<<frames, g.fft_threads, smem, st>>>(g, xbuf, Xre, Xim, P);
+  }
   SB_LAUNCH_CHECK();
   return true;
 }
@@ -401,8 +488,13 @@ bool launch_inverse(const GeoK& g, const float* Yre, const float* Yim, int frame
   KTimer kt_(kcInverse, st);
   if (frames <= 0) return true;
   const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
-  if (!set_fft_smem((const void*)inverse_kernel, smem)) return false;
-  inverse_kernel<<<frames, g.fft_threads, smem, st>>>(g, Yre, Yim, synth);
+  if (fft_vec_ok(g)) {
+    if (!set_fft_smem((const void*)inverse_kernel<true>, smem)) return false;
+    inverse_kernel<true><<<frames, g.fft_threads, smem, st>>>(g, Yre, Yim, synth);
+  } else {
+    if (!set_fft_smem((const void*)inverse_kernel<false>, smem)) return false;
+    inverse_kernel<false><<<frames, g.fft_threads, smem, st>>>(g, Yre, Yim, synth);
+  }
   SB_LAUNCH_CHECK();
   return true;
 }
