@@ -547,9 +547,19 @@ bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, b
   uint32_t pos = 0;
   bool host_pending = false;
   int last_b = 0;
+  // Host buffers: the first H2D and the last D2H of a call are not hidden behind kernels, so a
+  // call that spans several sub-calls starts and ends with a short one (1/8 of a sub-call).
+  // Sub-call boundaries never change the output (streaming equivalence).
+  const GeoK& gk = h->geo->k;
+  const uint32_t ramp = (uint32_t)(sub_call_frames(gk) / 8 > 64 ? sub_call_frames(gk) / 8 : 64) *
+                        (uint32_t)gk.hop;
   while (pos < n) {
     uint32_t m = n - pos;
     const uint32_t cap = max_sub_samples(h);
+    if (!device_io && n > cap) {
+      if (pos == 0 && ramp < cap) m = ramp;
+      else if (m <= cap && m > 2 * ramp) m -= ramp;
+    }
     if (m > cap) m = cap;
     if (!sub_begin(h, L)) return false;
     float* dst = L.xbuf + hist_len(h);
