@@ -253,7 +253,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = api.lib()
     if args.lanes or args.chunk_frames:
-        if not L.specbleach_b200_configure(args.chunk_frames or 4096, args.lanes or 4):
+        if not L.specbleach_b200_configure(args.chunk_frames or 0, args.lanes or 4):
             raise SystemExit("bench.py: specbleach_b200_configure failed: " + sb.last_error())
 
     chans = make_file(rank)

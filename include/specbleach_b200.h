@@ -35,9 +35,10 @@ void* specbleach_b200_host_alloc(size_t bytes);
 void specbleach_b200_host_free(void* p);
 
 /* Engine tuning (call before the first handle is created):
- * frames per internal sub-call (default: chosen per frame size so that the NLM
- * grids fill whole waves of SMs, ~4352 at 48 kHz / 50 ms) and number of lanes,
- * i.e. CUDA streams with private scratch spectrograms (default 4). */
+ * frames per internal sub-call (0 = automatic, the default: a whole number of NLM
+ * chunks whose grids fill whole waves of SMs, 6 x 2176 = 13056 frames at
+ * 48 kHz / 50 ms, ~1.5 GB of scratch per lane) and number of lanes, i.e. CUDA
+ * streams with private scratch spectrograms (default 4, allocated on first use). */
 bool specbleach_b200_configure(uint32_t chunk_frames, uint32_t lanes);
 
 /* Same contract as specbleach[_2d]_process, but `input`/`output` are DEVICE

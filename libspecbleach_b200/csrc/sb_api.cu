@@ -194,7 +194,14 @@ bool specbleach_b200_configure(uint32_t chunk_frames, uint32_t lanes) {
     sb::set_error_msg("specbleach_b200_configure must be called before the first process()");
     return false;
   }
-  if (chunk_frames < 32 || chunk_frames > 32768 || lanes < 1 || lanes > 32) return false;
+  if (chunk_frames != 0 && (chunk_frames < 32 || chunk_frames > 32768)) {
+    sb::set_error_msg("specbleach_b200_configure: chunk_frames must be 0 (automatic) or in [32, 32768]");
+    return false;
+  }
+  if (lanes < 1 || lanes > 32) {
+    sb::set_error_msg("specbleach_b200_configure: lanes must be in [1, 32]");
+    return false;
+  }
   c.chunk_frames = (int)chunk_frames;
   c.num_lanes = (int)lanes;
   return true;

@@ -152,8 +152,15 @@ static bool lane_ensure(Lane& L, const GeoK& g, int F) {
 int sub_call_frames(const GeoK& g) {
   const int c = ctx().chunk_frames;
   if (c > 0) return c;
-  int f = 2 * nlm3_chunk_targets(g.K);       // default: two full NLM chunks per sub-call
-  if (f > 8192) f = nlm3_chunk_targets(g.K); // large spectra: one chunk
+  // default: six full NLM chunks per sub-call (measured on configs[1]: 2 chunks 22.6k x
+  // realtime, 4: 23.0k, 6: 23.05k, 8: 23.04k, 12: 22.8k), fewer when a lane's buffers
+  // (~20 rows of Kp floats per frame) would pass 4 GB
+  const int chunk = nlm3_chunk_targets(g.K);
+  const long long max_frames = 4000000000ll / (80ll * (long long)g.Kp);
+  int nchunks = (int)(max_frames / chunk);
+  if (nchunks > 6) nchunks = 6;
+  if (nchunks < 1) nchunks = 1;
+  const int f = nchunks * chunk;
   return f < 32 ? 32 : f;
 }
 
