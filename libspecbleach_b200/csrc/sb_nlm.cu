@@ -748,12 +748,8 @@ bool launch_nlm(const GeoK& g, const float* S, int first_target_row, int targets
       return false;
     }
   } else if (nfull > 0 && variant == 2) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      SB_CUDA(cudaFuncSetAttribute((const void*)nlm2_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2));
-      attr_set = true;
-    }
+    SB_CUDA(cudaFuncSetAttribute((const void*)nlm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)SMEM2));   // per device, hence on every call
     dim3 grid((nfull + B2 - 1) / B2, (targets + TT2 - 1) / TT2);
     // rows of S that exist: the last target's +4 look-ahead row
     const int last_row = first_target_row + targets - 1 + kNlmFuture;

@@ -465,12 +465,9 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
                  float* Shat, cudaStream_t st) {
   const int nfull = g.K / 8;
   if (nfull <= 0 || targets <= 0) return true;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM3));
-    attr_set = true;
-  }
+  // per device and context, hence on every call rather than once per process
+  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)SMEM3));
   const int chunk = nlm3_chunk_targets(g.K);
   Scratch3 sc;
   {
@@ -497,6 +494,9 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
                                            last_row, h, sc.W, sc.F);
     SB_LAUNCH_CHECK();
     const int pairs = cnt * nfull;
+    // (paste on a side stream under the next chunk's distance kernel, two scratch sets: the NLM
+    // launch alone 3.5 % faster, the two-lane step unchanged -- the other lane already fills
+    // the ramps -- so the scratch stays single)
     nlm3_paste_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
                                                          first_target_row + t0, cnt, h, sc.W, sc.F,
                                                          Shat + (size_t)t0 * g.Kp, g.Kp);
