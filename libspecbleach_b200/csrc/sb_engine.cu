@@ -166,8 +166,11 @@ int sub_call_frames(const GeoK& g) {
 
 Lane* get_lane(int idx, const GeoK& g) {
   Context& c = ctx();
-  if ((int)c.lanes.size() < c.num_lanes) c.lanes.resize(c.num_lanes);
-  Lane& L = c.lanes[idx % c.num_lanes];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;   // callers select the handle's device first
+  std::vector<Lane>& lanes = c.lanes[dev];
+  if ((int)lanes.size() < c.num_lanes) lanes.resize(c.num_lanes);
+  Lane& L = lanes[idx % c.num_lanes];
   if (!lane_ensure(L, g, sub_call_frames(g))) return nullptr;
   return &L;
 }
@@ -644,8 +647,9 @@ bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* 
     if (!L) { ok = false; break; }
     ok = enqueue_call(h, *L, n[i], in[i], out[i], device_io);
   }
-  for (Lane& L : c.lanes)
-    if (L.stream) cudaStreamSynchronize(L.stream);
+  for (auto& dl : c.lanes)
+    for (Lane& L : dl.second)
+      if (L.stream) cudaStreamSynchronize(L.stream);
   for (uint32_t i = 0; i < count; i++)
     if (hs[i]) after_sync(hs[i]);
   if (ok) {
@@ -659,8 +663,9 @@ bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* 
 }
 
 bool stats_collect(Context& c) {
-  for (Lane& L : c.lanes)
-    if (L.stream) SB_CUDA(cudaStreamSynchronize(L.stream));
+  for (auto& dl : c.lanes)
+    for (Lane& L : dl.second)
+      if (L.stream) SB_CUDA(cudaStreamSynchronize(L.stream));
   SB_CUDA(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lock(g_kev_mu);
   for (KEvent& k : g_kevents) {

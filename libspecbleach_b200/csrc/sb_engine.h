@@ -3,14 +3,16 @@
 
 #include "sb_common.h"
 
+#include <map>
 #include <mutex>
+#include <vector>
 
 namespace sb {
 
 struct Context {
-  int chunk_frames = 0;      // frames per internal sub-call; 0 = two NLM chunks of the geometry
+  int chunk_frames = 0;      // frames per internal sub-call; 0 = automatic (sub_call_frames)
   int num_lanes = 4;
-  std::vector<Lane> lanes;
+  std::map<int, std::vector<Lane>> lanes;   // per device: streams and scratch belong to one GPU
   // instrumentation
   double nlm_ms = 0.0;
   uint64_t nlm_launches = 0;

@@ -205,3 +205,28 @@ def test_distinct_handles_from_concurrent_host_threads(gpu):
     assert not errs, errs
     for a, b in zip(want, got):
         assert np.array_equal(a, b)
+
+
+def test_handles_on_two_devices_of_one_process(gpu):
+    """specbleach_b200_set_device: handles created after it live on that device.  One process
+    per GPU is the intended deployment (bench.py, sharding.py), but a host that drives two
+    GPUs from one process gets the same samples from either (lanes, scratch and geometry
+    tables are per device)."""
+    import libspecbleach_b200 as sb
+    if sb.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    sr = 48000
+    x = synth(6.0, sr, 91)
+    try:
+        assert sb.set_device(0)
+        d0 = gpu.Denoiser(sr, 50.0, True)
+        assert sb.set_device(1)
+        d1 = gpu.Denoiser(sr, 50.0, True)
+        y1a = run_flow(d1, x, sr, P2D, 7777)
+        y0 = run_flow(d0, x, sr, P2D, 7777)
+        d1b = gpu.Denoiser(sr, 50.0, True)
+        y1b = run_flow(d1b, x, sr, P2D, 7777)
+    finally:
+        sb.set_device(0)
+    assert np.array_equal(y0, y1a)
+    assert np.array_equal(y0, y1b)
