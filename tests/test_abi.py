@@ -112,3 +112,22 @@ def test_wav_tool_is_built_and_prints_usage():
     assert tool.exists(), "run __graft_entry__.build()"
     r = subprocess.run([str(tool)], capture_output=True, text=True)
     assert r.returncode == 2 and "Usage" in r.stderr
+
+
+def test_configure_validates_its_arguments_without_a_gpu():
+    """engine tuning (include/specbleach_b200.h): 0 = automatic sub-call size, otherwise
+    [32, 32768] frames; 1..32 lanes; refusals carry a message.  Run in a child process so
+    the settings do not leak into other tests."""
+    code = (
+        "from libspecbleach_b200 import api\n"
+        "L = api.lib()\n"
+        "assert not L.specbleach_b200_configure(16, 4) and 'chunk_frames' in api.last_error()\n"
+        "assert not L.specbleach_b200_configure(40000, 4)\n"
+        "assert not L.specbleach_b200_configure(0, 0) and 'lanes' in api.last_error()\n"
+        "assert not L.specbleach_b200_configure(0, 33)\n"
+        "assert L.specbleach_b200_configure(0, 2)\n"
+        "assert L.specbleach_b200_configure(4096, 8)\n"
+        "print('ok')\n")
+    import sys
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
