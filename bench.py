@@ -362,10 +362,21 @@ def run_ours(args):
         nlm_s = st_dev["nlm_ms"] / 1e3
         achieved = nlm_flop / nlm_s / 1e12 if nlm_s > 0 else 0.0
         traffic = None
+        executed = None
         tf = ROOT / "profiles" / "nlm_traffic.json"
         if tf.exists():
             try:
-                per_target = json.loads(tf.read_text()).get("dram_bytes_per_target_frame")
+                tfj = json.loads(tf.read_text())
+                ex = tfj.get("distance_kernel_executed")
+                if ex:   # what the FP32 pipe really does (ncu SASS counts of the same capture)
+                    k = tfj["kernels"]["nlm3_kernel"]
+                    tflops = ex["fp32_flop_per_chunk"] / (k["time_us"] * 1e-6) / 1e12
+                    executed = {"tflops_in_distance_kernel": tflops,
+                                "frac_of_peak": tflops / fp32_peak if fp32_peak > 0 else None,
+                                "issue_active_pct": ex["issue_active_pct"],
+                                "fma_pipe_active_pct": ex["fma_pipe_active_pct"],
+                                "source": ex["source"]}
+                per_target = tfj.get("dram_bytes_per_target_frame")
                 blocks_per_frame = (1601 + 7) // 8
                 targets_per_launch = st_dev["nlm_frame_blocks"] / max(1, st_dev["nlm_launches"]) / blocks_per_frame
                 traffic = per_target * targets_per_launch
@@ -377,6 +388,7 @@ def run_ours(args):
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved / fp32_peak if fp32_peak > 0 else None,
             "traffic": traffic,
+            "executed": executed,
             "peak_source": "FFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no "
                            "FP32 figure; HBM %.0f GB/s measured is not the bound: ~60 KB/frame)"
                            % peaks.get("hbm_gbs", 0.0),
