@@ -235,6 +235,10 @@ __device__ __forceinline__ void walk_plain3(const Lane3& L, int dti, int ta, int
 // age[r] = partial distance of the target whose patch row r is the current row.  Every step the
 // partial sums move one age up THROUGH the add (age[r] = age[r-1] + term, evaluated from r = 7
 // down), so the loop needs neither register rotation nor unrolling: r0+r1+...+r7 in order.
+// The alias choice per patch row is a run-time select (72 FSEL per step, 7.5 % of the kernel's
+// instructions).  Measured alternatives: dt as a template parameter folds the selects but the
+// seven bodies (52 KB next to the 25 KB plain walker) thrash the 32 KB instruction cache, 3x
+// slower; a warp-uniform branch per row is 4 % slower than the selects.
 __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int ta, int tb, bool edge) {
   const int dt = dti - kNlmPast;
   int rlo = 0, rhi = 8, shift = 0;                   // rows r < rlo or r >= rhi use the alias
