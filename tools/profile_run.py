@@ -1,6 +1,6 @@
 """Small, fixed job for ncu: 2D NLM denoiser, 48 kHz mono, learn 1 s + denoise
-`seconds` (default 60 s -> 4800 frames: one full 4096-frame sub-call plus a
-remainder).  Same kernels and launch shapes as bench.py, ~60 launches.
+`seconds` (default 60 s -> 4800 frames, one sub-call: three NLM chunks of 2176 / 2176 / 448
+targets).  Same kernels as bench.py, ~40 launches.
 
     python tools/profile_run.py [seconds]
 """
