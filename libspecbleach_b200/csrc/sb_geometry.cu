@@ -74,7 +74,11 @@ static void fill_passes(GeoK& g) {
     if (resident < 24) cost *= 24.0 / resident;
     if (cost < best - 1e-9) { best = cost; g.fft_threads = T; }
   }
-  if (const char* e = getenv("SB_FFT_THREADS")) g.fft_threads = atoi(e);
+  // measurement knob: SB_FFT_THREADS=<32..512> overrides the choice
+  if (const char* e = getenv("SB_FFT_THREADS")) {
+    const int t = atoi(e);
+    if (t >= 32 && t <= 512) g.fft_threads = t;
+  }
 }
 
 static void factorize(int m, int* fac, int* nfac) {

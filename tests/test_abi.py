@@ -131,3 +131,21 @@ def test_configure_validates_its_arguments_without_a_gpu():
     import sys
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+def test_launch_share_summary_reads_the_committed_ncu_list():
+    """tools/ncu_summary.py --launches is what turns the ncu launch list under profiles/ into
+    the share table DESIGN.md quotes; the committed pair must stay consistent."""
+    import sys
+    lists = sorted((ROOT / "profiles").glob("r01*_launches_ncu.csv"))
+    assert lists, "no launch list under profiles/"
+    csv_path = lists[-1]
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), "--launches", str(csv_path), "cmd"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.splitlines()[2:] if ln.strip()]
+    assert rows[0][0] == "nlm3_kernel"                       # the dominant kernel
+    shares = {row[0]: float(row[-4].rstrip("%")) for row in rows}
+    assert abs(sum(shares.values()) - 100.0) < 1.0
+    committed = (ROOT / "profiles" / csv_path.name.replace("launches_ncu.csv", "launch_shares.txt")).read_text()
+    assert f"{shares['nlm3_kernel']:.1f}%" in committed
