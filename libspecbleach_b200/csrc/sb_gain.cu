@@ -1,7 +1,8 @@
 // Gain chain: everything between the (NLM-smoothed) spectrum and the gains that
-// multiply the delayed FFT frame.  Frame-parallel parts are ordinary
-// (frame, bin) / (frame, band) kernels; the three time recursions of the
-// masking veto are one-thread-per-bin / per-band sequential scans over frames.
+// multiply the delayed FFT frame.  Frame-parallel parts are (frame, bin) kernels
+// with one CTA per frame row and a thread per 4 bins, and (frame, band) kernels
+// with one CTA per frame; the three time recursions of the masking veto are
+// sequential scans over frames staged through shared memory (rowscan_kernel).
 //
 // Reference functions restated here (whole-batch form):
 //   get_morphed_profile            spectral_utils.c:253-279
