@@ -58,6 +58,26 @@ def config_dict(n_gpus: int) -> dict:
     }
 
 
+def pin_to_gpu_cpus(local: int) -> str | None:
+    """N > 1 only: bind this rank to the CPUs NVML names as local to its GPU before the pinned
+    host buffers are allocated, so that the H2D / D2H of eight ranks do not cross sockets.
+    Best effort: returns a description, or None when NVML or the affinity call is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to the {len(cpus)} CPUs local to its GPU (NVML)"
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def make_file(rank: int) -> list[np.ndarray]:
     from libspecbleach_b200.synth import speech_plus_noise
     return [speech_plus_noise(FILE_SECONDS, SR, 20260002 + 1000 * rank + ch) for ch in range(CHANNELS)]
@@ -248,7 +268,9 @@ def run_ours(args):
     if not sb.set_device(local):
         raise SystemExit("bench.py: " + sb.last_error())
     dist = None
+    affinity = None
     if world > 1:
+        affinity = pin_to_gpu_cpus(local)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = api.lib()
@@ -409,7 +431,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(world),
+            "data": "synthetic", "config": dict(config_dict(world), host_affinity=affinity),
             "e2e": {"value": e2e, "unit": "x realtime", "h2d_bytes_per_step": bytes_step,
                     "d2h_bytes_per_step": bytes_step, "ms_per_step": ms_e2e / args.steps,
                     "api": "specbleach_b200_process_batch (= specbleach_2d_process per channel), "
