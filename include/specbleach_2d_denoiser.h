@@ -4,6 +4,14 @@
  * ABI-identical to the reference's public header
  * (reference: include/specbleach_2d_denoiser.h:37-171).  See
  * specbleach_denoiser.h for the conventions.
+ *
+ * Attribution: the interface declared here (names, types, struct layout) is that of
+ * libspecbleach - A spectral processing library, Copyright 2022 Luciano Dato
+ * <lucianodato@gmail.com>, distributed under the GNU Lesser General Public License,
+ * version 2.1 or (at your option) any later version, WITHOUT ANY WARRANTY; see
+ * <https://www.gnu.org/licenses/old-licenses/lgpl-2.1.html>.  This header restates that
+ * interface so that programs written against libspecbleach link unchanged; it is
+ * distributed under the same licence.
  */
 #ifndef SPECBLEACH_2D_DENOISER_H_INCLUDED
 #define SPECBLEACH_2D_DENOISER_H_INCLUDED

@@ -8,6 +8,14 @@
  * batches by CUDA kernels on a B200.
  *
  * Error behaviour mirrors the reference: NULL / false / 0, never errno.
+ *
+ * Attribution: the interface declared here (names, types, struct layout) is that of
+ * libspecbleach - A spectral processing library, Copyright 2022 Luciano Dato
+ * <lucianodato@gmail.com>, distributed under the GNU Lesser General Public License,
+ * version 2.1 or (at your option) any later version, WITHOUT ANY WARRANTY; see
+ * <https://www.gnu.org/licenses/old-licenses/lgpl-2.1.html>.  This header restates that
+ * interface so that programs written against libspecbleach link unchanged; it is
+ * distributed under the same licence.
  */
 #ifndef SPECBLEACH_DENOISER_H_INCLUDED
 #define SPECBLEACH_DENOISER_H_INCLUDED

@@ -22,10 +22,15 @@ namespace sb {
 // estimator state layout in Handle::d_est (floats):
 //   [0] first-frame flag (1 = still waiting for the first non-silent frame)
 //   [1] Martin frame_count   [2] Martin subwin_index
+//   [8..10] the same three values as they stand AFTER the scan in flight: every CTA of a scan
+//        reads [0..2] when it starts, so the scan must not overwrite them (a CTA scheduled after
+//        CTA 0 has retired would see the next call's flag and counters); thread 0 leaves the new
+//        values here and header_commit_kernel moves them to [0..2] once the scan has finished
 //   [32 ...] per-bin arrays, pitch Kp:
 //        SPP:    psd, smoothed_spp
 //        Martin: psd, cur_min, hist[8]
 constexpr int kEstHeader = 32;
+constexpr int kEstNext = 8;
 constexpr int kBatch = 16;   // frames whose loads are in flight per thread in the scans
 
 namespace {
@@ -128,7 +133,15 @@ __global__ void spp_scan_kernel(const GeoK g, const float* __restrict__ P,
   }
   a[k] = psd;
   a[g.Kp + k] = sspp;
-  if (k == 0) est[0] = first ? 1.f : 0.f;
+  if (k == 0) {
+    est[kEstNext + 0] = first ? 1.f : 0.f;
+    est[kEstNext + 1] = est[1];
+    est[kEstNext + 2] = est[2];
+  }
+}
+
+__global__ void header_commit_kernel(float* __restrict__ est) {
+  if (threadIdx.x < 3) est[threadIdx.x] = est[kEstNext + threadIdx.x];
 }
 
 __global__ void martin_scan_kernel(const GeoK g, const float* __restrict__ P,
@@ -210,9 +223,9 @@ __global__ void martin_scan_kernel(const GeoK g, const float* __restrict__ P,
 #pragma unroll
   for (int d = 0; d < kMartinSubwinCount; d++) a[(size_t)(2 + d) * g.Kp + k] = hist[d];
   if (k == 0) {
-    est[0] = first ? 1.f : 0.f;
-    est[1] = (float)fc;
-    est[2] = (float)idx;
+    est[kEstNext + 0] = first ? 1.f : 0.f;
+    est[kEstNext + 1] = (float)fc;
+    est[kEstNext + 2] = (float)idx;
   }
 }
 
@@ -250,7 +263,11 @@ bool launch_adaptive(const GeoK& g, int method, const float* P, int frames, cons
     martin_scan_kernel<<<(g.K + 63) / 64, 64, 0, st>>>(g, P, energy, frames, floorv, est,
                                                        noise_rows);
   }
-  if (method != kBrandt) SB_LAUNCH_CHECK();
+  if (method != kBrandt) {
+    SB_LAUNCH_CHECK();
+    header_commit_kernel<<<1, 32, 0, st>>>(est);
+    SB_LAUNCH_CHECK();
+  }
   return launch_interp_smooth(g, noise_rows, g.Kp, frames, 0xffffffffu, kInterpThreshold,
                               kNoiseSmoothing, floorv, st);
 }

@@ -189,6 +189,7 @@ void specbleach_b200_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 bool specbleach_b200_configure(uint32_t chunk_frames, uint32_t lanes) {
+  std::lock_guard<std::recursive_mutex> engine_lock(sb::engine_mutex());
   sb::Context& c = sb::ctx();
   if (!c.lanes.empty()) {
     sb::set_error_msg("specbleach_b200_configure must be called before the first process()");

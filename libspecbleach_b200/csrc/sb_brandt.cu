@@ -396,12 +396,11 @@ bool launch_brandt(const GeoK& g, const float* P, int frames, const float* floor
     return false;
   }
   const size_t smem = per_warp * (size_t)wpb;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  // the attribute belongs to the (device, context) pair: set it on every call, as launch_nlm3
+  // does, so that handles on several GPUs of one process all get it
+  if (smem > 48 * 1024)
     SB_CUDA(cudaFuncSetAttribute((const void*)brandt_eval_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   dim3 grid((g.K + wpb - 1) / wpb, (frames + kBrandtTile - 1) / kBrandtTile);
   brandt_eval_kernel<<<grid, 32 * wpb, smem, st>>>(g, c, P, floorv, est, idx, fresh_seed ? 1 : 0,
                                                    wpb, noise_rows);

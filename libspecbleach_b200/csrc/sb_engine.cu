@@ -217,6 +217,8 @@ Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms) {
 void handle_destroy(Handle* h) {
   std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   if (!h) return;
+  DeviceGuard restore_device;
+  cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   float* bufs[] = {h->d_prof, h->d_med_ring, h->d_hist, h->d_tail[0], h->d_tail[1],
                    h->d_X_hist_re, h->d_X_hist_im, h->d_noise_hist, h->d_S_hist, h->d_stable,
@@ -248,6 +250,9 @@ bool handle_load_parameters(Handle* h, const Params& p) {
     }
     if (h->est_method != requested) {
       const GeoK& g = h->geo->k;
+      DeviceGuard restore_device;           // the estimator state lives on the handle's GPU
+      SB_CUDA(cudaSetDevice(h->device));
+      SB_CUDA(cudaDeviceSynchronize());     // a lane may still read the old estimator
       if (h->d_est) cudaFree(h->d_est);
       h->d_est = nullptr;
       h->est_floats = estimator_floats(g, requested);
@@ -269,6 +274,7 @@ bool handle_load_parameters(Handle* h, const Params& p) {
 }
 
 bool handle_load_profile(Handle* h, const float* prof, uint32_t size, uint32_t blocks, int mode) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   if (size != h->profile_size || mode < 1 || mode > 4) return false;
   memcpy(h->prof_host[mode - 1].data(), prof, size * sizeof(float));
   h->block_count[mode - 1] = blocks;
@@ -280,6 +286,7 @@ bool handle_load_profile(Handle* h, const float* prof, uint32_t size, uint32_t b
 }
 
 void handle_reset_profile(Handle* h) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   for (int m = 0; m < 4; m++) {
     std::fill(h->prof_host[m].begin(), h->prof_host[m].end(), 0.f);
     h->block_count[m] = 0;
@@ -619,6 +626,7 @@ bool process_call(Handle* h, uint32_t n, const float* in, float* out, bool devic
     p.tonal = 0.0f;    // spectral_2d_denoiser.c:174
     h->prm = p;
   }
+  DeviceGuard restore_device;
   SB_CUDA(cudaSetDevice(h->device));
   Lane* L = get_lane(0, h->geo->k);
   if (!L) return false;
@@ -635,6 +643,7 @@ bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* 
                    float* const* out, bool device_io) {
   std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   if (count == 0) return true;
+  DeviceGuard restore_device;
   Context& c = ctx();
   bool ok = true;
   // handles are dealt round-robin to lanes; each lane serialises its own

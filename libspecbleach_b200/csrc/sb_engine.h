@@ -27,6 +27,14 @@ int sub_call_frames(const GeoK& g);   // chunk_frames, or its per-geometry defau
 
 void set_error_msg(const char* msg);
 
+// Entry points select the handle's device; the caller's current device is put back on return
+// (a library call must not change it behind the host program's back).
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms);
 void handle_destroy(Handle* h);
 bool handle_load_parameters(Handle* h, const Params& p);

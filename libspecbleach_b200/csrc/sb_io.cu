@@ -167,8 +167,18 @@ bool state_save(Handle* h, void* blob, size_t bytes) {
     set_error_msg("specbleach-b200: state buffer too small (see specbleach_b200_state_size)");
     return false;
   }
+  DeviceGuard restore_device;
   SB_CUDA(cudaSetDevice(h->device));
   SB_CUDA(cudaDeviceSynchronize());
+  // load_noise_profile_for_mode / reset_noise_profile / profile_load since the last process():
+  // the host mirror is newer than d_prof, and the blob must hold ONE profile, not two
+  if (h->host_dirty) {
+    const GeoK& g = h->geo->k;
+    for (int m = 0; m < 4; m++)
+      SB_CUDA(cudaMemcpy(h->d_prof + (size_t)m * g.Kp, h->prof_host[m].data(),
+                         g.K * sizeof(float), cudaMemcpyHostToDevice));
+    h->host_dirty = false;
+  }
   unsigned char* p = static_cast<unsigned char*>(blob);
   StateHeader hd;
   memset(&hd, 0, sizeof(hd));
@@ -234,23 +244,36 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
     set_error_msg("specbleach-b200: state blob was saved for another denoiser geometry");
     return false;
   }
-  SB_CUDA(cudaSetDevice(h->device));
-  SB_CUDA(cudaDeviceSynchronize());
-  // the estimator of the snapshot decides the layout of d_est
+  // Validate the whole blob before the live handle is touched: a truncated or corrupt blob must
+  // leave it exactly as it was.
+  const GeoK& gk = h->geo->k;
   StateScalars sc;
   memcpy(&sc, p + sizeof(hd), sizeof(sc));
-  if ((int)hd.est_method != h->est_method || (hd.est_floats != 0) != (h->d_est != nullptr)) {
-    if (h->d_est) cudaFree(h->d_est);
-    h->d_est = nullptr;
-    h->est_floats = 0;
-    h->est_method = (int)hd.est_method;
-    if (hd.est_floats) {
-      SB_CUDA(cudaMalloc(&h->d_est, hd.est_floats * sizeof(float)));
-      h->est_floats = hd.est_floats;
-    }
+  const int new_method = (int)hd.est_method;     // -1 (0xffffffff): no estimator created yet
+  if (new_method != -1 && new_method != kSpp && new_method != kBrandt && new_method != kMartin) {
+    set_error_msg("specbleach-b200: state blob names an unknown noise estimator");
+    return false;
+  }
+  const uint64_t want_est = (new_method == -1) ? 0 : (uint64_t)estimator_floats(gk, new_method);
+  if (hd.est_floats != want_est || hd.frame != (uint32_t)gk.frame || hd.hop != (uint32_t)gk.hop) {
+    set_error_msg("specbleach-b200: state blob does not fit this geometry (estimator size / frame / hop)");
+    return false;
+  }
+  if (new_method == kBrandt && !brandt_supported(gk)) {
+    set_error_msg("specbleach-b200: Brandt history too long for this frame size");
+    return false;
   }
   size_t need = sizeof(hd) + sizeof(sc) + 4 + 4 * (size_t)h->profile_size * sizeof(float);
-  for (const DevArray& d : state_arrays(h)) need += d.floats * sizeof(float);
+  {
+    // the array list of the handle AS IT WILL BE: same as now except for the estimator
+    float* keep = h->d_est;
+    const size_t keep_n = h->est_floats;
+    h->d_est = nullptr;
+    for (const DevArray& d : state_arrays(h)) need += d.floats * sizeof(float);
+    h->d_est = keep;
+    h->est_floats = keep_n;
+    need += (size_t)want_est * sizeof(float);
+  }
   if (bytes < need) {
     set_error_msg("specbleach-b200: state blob truncated");
     return false;
@@ -260,6 +283,24 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
   if (c != crc32(blob, need - 4)) {
     set_error_msg("specbleach-b200: state blob checksum mismatch");
     return false;
+  }
+  if (sc.med_write < 0 || sc.med_write >= kMedianFrames || sc.tail_cur < 0 || sc.tail_cur > 1 ||
+      sc.carry >= (uint32_t)gk.hop) {
+    set_error_msg("specbleach-b200: state blob holds out-of-range ring positions");
+    return false;
+  }
+  DeviceGuard restore_device;
+  SB_CUDA(cudaSetDevice(h->device));
+  SB_CUDA(cudaDeviceSynchronize());
+  // commit: the estimator of the snapshot decides the layout of d_est
+  if (new_method != h->est_method || (want_est != 0) != (h->d_est != nullptr) ||
+      (size_t)want_est != h->est_floats) {
+    float* fresh = nullptr;
+    if (want_est) SB_CUDA(cudaMalloc(&fresh, (size_t)want_est * sizeof(float)));
+    if (h->d_est) cudaFree(h->d_est);
+    h->d_est = fresh;
+    h->est_floats = (size_t)want_est;
+    h->est_method = new_method;
   }
   p += sizeof(hd) + sizeof(sc);
   h->prm = sc.prm;
@@ -285,7 +326,7 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
     SB_CUDA(cudaMemcpy(*d.ptr, p, d.floats * sizeof(float), cudaMemcpyHostToDevice));
     p += d.floats * sizeof(float);
   }
-  h->host_dirty = false;          // d_prof came with the snapshot
+  h->host_dirty = false;          // d_prof came with the snapshot (state_save syncs it first)
   h->profile_dl_pending = false;
   h->noise_version++;             // cached tonal mask / whitening rows are stale
   for (int r = 0; r < 4; r++) h->noise_hist_version[r] = 0;
@@ -363,6 +404,7 @@ bool process_interleaved(Handle** hs, uint32_t channels, uint32_t frames, int fo
   if (!hs || channels == 0 || frames == 0 || !in || !out || format < 0 || format > 3) return false;
   for (uint32_t c = 0; c < channels; c++)
     if (!hs[c]) return false;
+  DeviceGuard restore_device;
   SB_CUDA(cudaSetDevice(hs[0]->device));
   const size_t bytes = (size_t)frames * channels * pcm_bytes(format);
   const size_t pitch = ((size_t)frames + 31) & ~(size_t)31;

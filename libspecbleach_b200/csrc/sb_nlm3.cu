@@ -477,7 +477,8 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     Scratch3& ref = g_scratch[st];
-    const size_t need = (size_t)chunk * (size_t)nfull;
+    // sized for the largest chunk seen on this stream (small sub-calls keep it small)
+    const size_t need = (size_t)(targets < chunk ? targets : chunk) * (size_t)nfull;
     if (ref.pairs < need) {
       SB_CUDA(cudaStreamSynchronize(st));
       if (ref.W) cudaFree(ref.W);

@@ -60,6 +60,44 @@ def run_flow(d, x, learn, params, chunk):
     return np.concatenate(ys)
 
 
+# which branch each Brandt comparison took (reported and bounded by
+# test_gpu_parity.py::test_brandt_fallback_budget, the last test of that file)
+BRANDT_BRANCHES: dict[str, str] = {}
+
+
+def run_script(d, x, script, chunk):
+    """Drives one handle (reference build or CUDA path: same method names) through a list of
+    steps on consecutive segments of `x`.  A step is (seconds, action, kwargs):
+      "params"  -> load_parameters(**kwargs), then process the segment
+      "none"    -> process the segment without touching the parameters
+      "reset"   -> reset_profile(), load_parameters(**kwargs), process
+      "load"    -> load_profile(arrays from kwargs["profiles"]) then load_parameters(kwargs["params"])
+    Returns the concatenated output."""
+    sr = script["sr"]
+    pos = 0
+    ys = []
+    for seconds, action, kw in script["steps"]:
+        n = int(round(seconds * sr))
+        seg = x[pos:pos + n]
+        assert seg.shape[0] == n, "script longer than the input"
+        if action == "params":
+            assert d.load_parameters(**kw)
+        elif action == "reset":
+            assert d.reset_profile()
+            assert d.load_parameters(**kw)
+        elif action == "load":
+            for mode, (arr, blocks) in kw["profiles"].items():
+                a = np.zeros(d.profile_size(), np.float32)
+                a[:arr.shape[0]] = arr
+                assert d.load_profile(a, blocks, mode)
+            assert d.load_parameters(**kw["params"])
+        elif action != "none":
+            raise ValueError(action)
+        ys.append(d.process(seg, chunk))
+        pos += n
+    return np.concatenate(ys)
+
+
 def assert_parity_discontinuous(got, make_ref, x, what="", trials=3):
     """Parity for the Brandt estimator, whose arg-min over five fits and 0.90 confidence
     gate are discontinuous: when two fits tie to ~1e-7 the reference's own choice flips
@@ -70,6 +108,8 @@ def assert_parity_discontinuous(got, make_ref, x, what="", trials=3):
     want = make_ref(x)
     err, snr = parity(got, want)
     if err <= MAX_ABS_TOL and snr >= SNR_TOL_DB:
+        BRANDT_BRANCHES[what] = "exact-input reference (%.2e / %.1f dB)" % (err, snr)
+        print(f"[brandt] {what}: {BRANDT_BRANCHES[what]}")
         return "exact-input reference", err, snr
     rng = np.random.default_rng(1)
     best = (err, snr)
@@ -82,6 +122,10 @@ def assert_parity_discontinuous(got, make_ref, x, what="", trials=3):
         if e <= MAX_ABS_TOL and s_ >= SNR_TOL_DB:
             assert e_self > MAX_ABS_TOL or s_self < SNR_TOL_DB, \
                 f"{what}: reference is stable here, yet the CUDA path misses it ({err:.3e}, {snr:.1f} dB)"
+            BRANDT_BRANCHES[what] = ("FALLBACK: 1-ULP-perturbed reference (%.2e / %.1f dB; exact input "
+                                     "%.2e / %.1f dB; reference vs itself %.1f dB)"
+                                     % (e, s_, err, snr, s_self))
+            print(f"[brandt] {what}: {BRANDT_BRANCHES[what]}")
             return "1-ULP-perturbed reference (reference unstable: %.1f dB vs itself)" % s_self, e, s_
     raise AssertionError(f"{what}: max_abs={err:.3e} snr={snr:.1f} dB vs the reference; "
                          f"best vs perturbed references {best[0]:.3e} / {best[1]:.1f} dB")

@@ -149,3 +149,34 @@ def test_launch_share_summary_reads_the_committed_ncu_list():
     assert abs(sum(shares.values()) - 100.0) < 1.0
     committed = (ROOT / "profiles" / csv_path.name.replace("launches_ncu.csv", "launch_shares.txt")).read_text()
     assert f"{shares['nlm3_kernel']:.1f}%" in committed
+
+
+def test_library_identity_matches_the_reference_install():
+    """src/meson.build:27-44: library('specbleach', soversion '0') + pkg-config 'libspecbleach'.
+    The build gives the product the reference's SONAME, the soname / development links next to it
+    and a libspecbleach.pc, so `-lspecbleach` and an existing DT_NEEDED libspecbleach.so.0 resolve
+    to it."""
+    import re
+    import shutil
+    import subprocess
+    libdir = ROOT / "libspecbleach_b200"
+    so = libdir / "libspecbleach_b200.so"
+    for name in ("libspecbleach.so.0", "libspecbleach.so"):
+        assert (libdir / name).exists(), name
+        assert (libdir / name).stat().st_size == so.stat().st_size
+    pc = (libdir / "libspecbleach.pc").read_text()
+    assert re.search(r"^Name: libspecbleach$", pc, re.M) and re.search(r"^Version: 0\.3\.0$", pc, re.M)
+    assert "-lspecbleach" in pc
+    if shutil.which("readelf"):
+        dyn = subprocess.run(["readelf", "-d", str(so)], capture_output=True, text=True).stdout
+        assert "soname: [libspecbleach.so.0]" in dyn
+        exe = ROOT / "oracle" / "_ref" / "api_tests" / "test_integration"
+        if exe.exists():
+            dyn = subprocess.run(["readelf", "-d", str(exe)], capture_output=True, text=True).stdout
+            assert "[libspecbleach.so.0]" in dyn
+
+
+def test_public_headers_carry_the_lgpl_attribution():
+    for name in ("specbleach_denoiser.h", "specbleach_2d_denoiser.h"):
+        text = (ROOT / "include" / name).read_text()
+        assert "Luciano Dato" in text and "Lesser General Public" in text

@@ -230,3 +230,48 @@ def test_handles_on_two_devices_of_one_process(gpu):
         sb.set_device(0)
     assert np.array_equal(y0, y1a)
     assert np.array_equal(y0, y1b)
+
+
+def test_config1_speech_wav_demo_flow(gpu, ref, tmp_path):
+    """BASELINE configs[0] as SURVEY 8d defines it: the 1D denoiser on the reference's own test
+    recording tests/test_data/Speech.wav (44.1 kHz float32 mono, 16.2 s; a git-ignored copy under
+    oracle/_ref/test_data travels to the GPU box) with the flow of examples/denoiser_demo.c:91-99,
+    234-300: learn on 8 blocks of 512 samples, then reduction 20 dB, whitening 50 %, smoothing 0,
+    masking depth 0.5, aggressiveness 1.0 in 512-sample blocks at the demo's 50 ms frames.
+    Compared: the reference build, the C API in 512-sample calls, and tools/sb_denoise --1d."""
+    import subprocess
+    import time
+    from pathlib import Path
+    from scipy.io import wavfile
+    root = Path(__file__).resolve().parent.parent
+    wav = root / "oracle" / "_ref" / "test_data" / "Speech.wav"
+    tool = root / "tools" / "sb_denoise"
+    if not wav.exists() or not tool.exists():
+        pytest.skip("oracle/_ref/test_data/Speech.wav or tools/sb_denoise missing (run __graft_entry__.build())")
+    sr, x = wavfile.read(str(wav))
+    assert sr == 44100 and x.dtype == np.float32 and x.ndim == 1 and x.shape[0] == 714355
+    learn, block = 8 * 512, 512
+    prm = dict(learn_noise=0, residual_listen=False, reduction_amount=20.0, smoothing_factor=0.0,
+               whitening_factor=50.0, masking_depth=0.5, aggressiveness=1.0)
+    r = ref.RefDenoiser(sr, 50.0, False)
+    t0 = time.perf_counter()
+    want = run_flow(r, x, learn, prm, block)
+    t_ref = time.perf_counter() - t0
+    assert r.profile_available(1)                      # the demo's own check after learning (:268-272)
+    d = gpu.Denoiser1D(sr, 50.0)
+    t0 = time.perf_counter()
+    got = run_flow(d, x, learn, prm, block)
+    t_gpu = time.perf_counter() - t0
+    assert d.profile_available(1) and d.block_count(1) == r.block_count(1) == learn // 551
+    err, snr = assert_parity(got, want, "config 1 (Speech.wav, demo flow)")
+    out = tmp_path / "speech_denoised.wav"
+    cmd = [str(tool), "--1d", "--frame-size", "50", "--learn-samples", str(learn), "--reduction", "20",
+           "--whitening", "50", "--smoothing", "0", "--masking", "0.5", "--aggressiveness", "1.0",
+           str(wav), str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    sr2, y = wavfile.read(str(out))
+    assert sr2 == sr and y.dtype == np.float32 and y.shape == x.shape
+    assert np.array_equal(y, got)                      # tool == API, bit for bit (chunking-invariant)
+    print(f"config 1: max_abs={err:.3e} snr={snr:.1f} dB; reference {x.shape[0] / sr / t_ref:.1f}x realtime "
+          f"(1 thread, 512-sample calls), CUDA path through 512-sample calls {x.shape[0] / sr / t_gpu:.1f}x")

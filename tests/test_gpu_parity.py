@@ -95,6 +95,10 @@ CASES = [
     ("2d_h2_whit100", True, 48000, 50.0, dict(P2D, smoothing_factor=2.0, whitening_factor=100.0), None),
     ("1d_manual", False, 48000, 50.0, P1D, None),
     ("1d_smooth0_chunk512", False, 48000, 50.0, dict(P1D, smoothing_factor=0.0), 512),
+    ("1d_tonal12", False, 48000, 50.0, dict(P1D, tonal_reduction=12.0), 4800),
+    ("1d_tonal6_residual", False, 48000, 50.0, dict(P1D, tonal_reduction=6.0, residual_listen=True,
+                                                     aggressiveness=-0.3), 999),
+    ("1d_residual_44k1_20ms", False, 44100, 20.0, dict(P1D, residual_listen=True), None),
     ("2d_44k1_20ms", True, 44100, 20.0, P2D, 3001),
     ("1d_44k1_50ms", False, 44100, 50.0, P1D, None),
     ("2d_96k_77ms", True, 96000, 77.0, dict(P2D, tonal_reduction=12.0, nlm_masking_protection=1.0,

@@ -49,13 +49,17 @@ static bool read_wav(const char* path, Wav& w, std::string& err) {
   while (pos + 8 <= all.size()) {
     const uint32_t sz = rd32(&all[pos + 4]);
     if (memcmp(&all[pos], "fmt ", 4) == 0 && sz >= 16) {
+      if (pos + 8 + 16 > all.size()) { err = "fmt chunk truncated"; return false; }
       const unsigned char* p = &all[pos + 8];
       w.format_tag = rd16(p);
       w.channels = rd16(p + 2);
       w.sample_rate = rd32(p + 4);
       w.block_align = rd16(p + 12);
       w.bits = rd16(p + 14);
-      if (w.format_tag == 0xFFFE && sz >= 26) w.format_tag = rd16(p + 24);   // WAVE_FORMAT_EXTENSIBLE
+      if (w.format_tag == 0xFFFE && sz >= 26) {                              // WAVE_FORMAT_EXTENSIBLE
+        if (pos + 8 + 26 > all.size()) { err = "fmt chunk truncated"; return false; }
+        w.format_tag = rd16(p + 24);
+      }
       have_fmt = true;
     } else if (memcmp(&all[pos], "data", 4) == 0) {
       if (!have_fmt) { err = "data chunk before fmt chunk"; return false; }
@@ -89,8 +93,9 @@ static void usage(const char* prog) {
           "  --1d                   specbleach_denoiser (default: specbleach_2d_denoiser, NLM)\n"
           "  --frame-size <ms>      frame size (default 50)\n"
           "  --learn-seconds <s>    learn the noise profile on the first s seconds (default 1.0)\n"
+          "  --learn-samples <n>    the same in samples (the demo's 8 blocks of 512: 4096)\n"
           "  --load-profile <file>  restore a saved profile instead of learning\n"
-          "  --save-profile <file>  save the learned profile (channel 0)\n"
+          "  --save-profile <file>  save the learned profile (channel 0) as the denoise pass used it\n"
           "  --reduction <dB>       (default 20)      --whitening <%%>   (default 50)\n"
           "  --smoothing <val>      1D: %%, 2D: NLM h (default 0 / 1)\n"
           "  --masking <0..1>       masking depth / NLM masking protection (default 0.5)\n"
@@ -107,6 +112,7 @@ int main(int argc, char** argv) {
   float frame_ms = 50.f, learn_seconds = 1.f, reduction = 20.f, whitening = 50.f, smoothing = -1.f;
   float masking = 0.5f, strength = 50.f, aggr = 2.f, tonal = 0.f;
   int method = 0, device = 0;
+  long learn_samples = -1;
   const char *load_profile = nullptr, *save_profile = nullptr;
   std::vector<const char*> pos;
   for (int i = 1; i < argc; i++) {
@@ -115,6 +121,7 @@ int main(int argc, char** argv) {
     if (a == "--1d") two_d = false;
     else if (a == "--frame-size") val(frame_ms);
     else if (a == "--learn-seconds") val(learn_seconds);
+    else if (a == "--learn-samples" && i + 1 < argc) learn_samples = atol(argv[++i]);
     else if (a == "--reduction") val(reduction);
     else if (a == "--whitening") val(whitening);
     else if (a == "--smoothing") val(smoothing);
@@ -147,8 +154,15 @@ int main(int argc, char** argv) {
   else { fprintf(stderr, "unsupported WAV sample format (tag %u, %u bits)\n", w.format_tag, w.bits); return 1; }
   const uint32_t ch = w.channels;
   const size_t bps = w.bits / 8;
+  if (ch == 0 || w.sample_rate == 0) { fprintf(stderr, "fmt chunk: no channels / sample rate\n"); return 1; }
+  if (w.block_align != ch * bps) {
+    fprintf(stderr, "fmt chunk: block align %u is not channels x bytes per sample (%u x %zu)\n",
+            w.block_align, ch, bps);
+    return 1;
+  }
+  if (w.data.size() / (bps * ch) > 0xffffffffull) { fprintf(stderr, "data chunk too long\n"); return 1; }
   const uint32_t frames = (uint32_t)(w.data.size() / (bps * ch));
-  if (ch == 0 || frames == 0) { fprintf(stderr, "empty audio\n"); return 1; }
+  if (frames == 0) { fprintf(stderr, "empty audio\n"); return 1; }
 
   if (specbleach_b200_device_count() < 1 || !specbleach_b200_set_device(device)) {
     fprintf(stderr, "no CUDA device: %s\n", specbleach_b200_last_error());
@@ -192,7 +206,8 @@ int main(int argc, char** argv) {
         return 1;
       }
   } else if (!adaptive || learn_seconds > 0.f) {
-    learn_frames = (uint32_t)(learn_seconds * (float)w.sample_rate);
+    learn_frames = learn_samples >= 0 ? (uint32_t)learn_samples
+                                      : (uint32_t)(learn_seconds * (float)w.sample_rate);
     if (learn_frames > frames) learn_frames = frames;
   }
   if (learn_frames) {
@@ -200,8 +215,6 @@ int main(int argc, char** argv) {
       fprintf(stderr, "learn pass failed: %s\n", specbleach_b200_last_error());
       return 1;
     }
-    if (save_profile && !specbleach_b200_profile_save(hs[0], save_profile))
-      fprintf(stderr, "warning: could not save the profile: %s\n", specbleach_b200_last_error());
   }
   if (frames > learn_frames) {
     const size_t off = (size_t)learn_frames * ch * bps;
@@ -210,6 +223,17 @@ int main(int argc, char** argv) {
       fprintf(stderr, "denoise pass failed: %s\n", specbleach_b200_last_error());
       return 1;
     }
+  }
+  // The file holds the profile as the denoise pass used it: the first denoised frame refines the
+  // learned arrays (gap interpolation + smoothing, denoiser_profile_core.c:42-48), and a profile
+  // restored with --load-profile is taken as is.  Saved before any frame was denoised (input not
+  // longer than the learn segment) it would be the raw learned profile; the tool says so.
+  if (save_profile && learn_frames) {
+    if (frames <= learn_frames)
+      fprintf(stderr, "note: %s holds the unrefined profile (nothing was denoised after learning)\n",
+              save_profile);
+    if (!specbleach_b200_profile_save(hs[0], save_profile))
+      fprintf(stderr, "warning: could not save the profile: %s\n", specbleach_b200_last_error());
   }
   for (uint32_t c = 0; c < ch; c++) {
     if (two_d) specbleach_2d_free(hs[c]);
