@@ -59,7 +59,9 @@ static void fill_passes(GeoK& g) {
     for (int f = 0; f < g.nfac; f++) {
       const int r = g.fac[f];
       const bool hard = r == 2 || r == 3 || r == 4 || r == 5;
-      const int items = hard ? g.pass_nbf[f] : g.M;
+      // generic radix: a work item is a butterfly and a pair of outputs, (r - 1) / 2 terms of
+      // four double FMAs each (sb_stft.cu)
+      const int items = hard ? g.pass_nbf[f] : g.pass_nbf[f] * ((r + 1) / 2);
       cost += (double)((items + T - 1) / T) * warps * (hard ? r : 2.0 * r);
     }
     cost += 2.0 * (double)((g.M + T - 1) / T) * warps * 2.0;      // load and split / crop loops

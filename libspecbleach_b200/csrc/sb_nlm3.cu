@@ -35,6 +35,8 @@
 // Compiled with -ftz=true (the reference runs NLM under FTZ|DAZ).
 #include "sb_common.h"
 
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 
@@ -274,9 +276,167 @@ __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int ta, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed form of the row walk (sm_100a FFMA2 / FADD2: two FP32 operations per issue slot on an
+// aligned register pair; tools/microbench/fp32_pipes.cu: same FLOP rate as FFMA, half the issue
+// slots).  The distance kernel is issue-bound (75 % issue active, FMA pipe 52 %, 66 % of its
+// instructions FADD / FFMA), so halving the FP32 issue slots is what is left to gain.
+//  * row term of an even candidate c = 2m: the pairs (q, q+1), q = 0, 2, 4, 6 of target and
+//    partner are aligned register pairs of the LDS.128 results: 4 FADD2 + 4 FFMA2, then x + y;
+//  * odd candidate c = 2m + 1: the partner pairs (c+q, c+q+1) are aligned for ODD q, so the
+//    target is also kept shifted by one ((t1,t2) (t3,t4) (t5,t6): 6 register moves per row):
+//    3 FADD2 + 3 FFMA2, and the two end elements q = 0, 7 as scalar FADD + FFMA into x and y;
+//  * the delay tree and the wrapped walker's age update add candidate PAIRS (c, c+1).
+// Per plain row step 110 instead of 171 FP32-pipe issue slots.  The sums associate differently
+// from the scalar form ((q even) + (q odd)), deterministically.
+// ---------------------------------------------------------------------------------------------
+struct RowT {          // row terms / distances of the 9 candidates: pairs (0,1) (2,3) (4,5) (6,7), and 8
+  float2 p[4];
+  float s;
+};
+
+// a - b on a register pair.  sub.f32x2 is one FADD2 with the negate modifier on b; written as
+// __fadd2_rn(a, -b) the compiler hoists the negations of the shared partner pairs into 16 extra
+// FADD per row.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 sqdiff2(float2 t, float2 sgm, float2 r) {
+  const float2 d = sub2(t, sgm);
+  return __ffma2_rn(d, d, r);
+}
+__device__ __forceinline__ float2 sqdiff2_first(float2 t, float2 sgm) {
+  const float2 d = sub2(t, sgm);
+  return __fmul2_rn(d, d);
+}
+
+__device__ __forceinline__ void rowterms3p(const Lane3& L, int ra, int rp, RowT& R) {
+  rp = rp < 0 ? 0 : (rp > ROWS3 - 1 ? ROWS3 - 1 : rp);
+  const float4* pt = reinterpret_cast<const float4*>(L.tile + ra * PITCH3 + L.col_tg);
+  const float4* ps = reinterpret_cast<const float4*>(L.tile + rp * PITCH3 + L.col_seg);
+  const float4 t0 = pt[0], t1 = pt[1];
+  const float4 s0 = ps[0], s1 = ps[1], s2 = ps[3], s3 = ps[4];   // two 12-float column groups
+  const float2 T[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y),
+                       make_float2(t1.z, t1.w)};
+  const float2 To[3] = {make_float2(t0.y, t0.z), make_float2(t0.w, t1.x), make_float2(t1.y, t1.z)};
+  const float2 S2[8] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y),
+                        make_float2(s1.z, s1.w), make_float2(s2.x, s2.y), make_float2(s2.z, s2.w),
+                        make_float2(s3.x, s3.y), make_float2(s3.z, s3.w)};
+  float r[NC3];
+#pragma unroll
+  for (int m = 0; m < 5; m++) {           // even candidates c = 2m
+    float2 a = sqdiff2_first(T[0], S2[m]);
+    a = sqdiff2(T[1], S2[m + 1], a);
+    a = sqdiff2(T[2], S2[m + 2], a);
+    a = sqdiff2(T[3], S2[m + 3], a);
+    r[2 * m] = a.x + a.y;
+  }
+#pragma unroll
+  for (int m = 0; m < 4; m++) {           // odd candidates c = 2m + 1
+    float2 a = sqdiff2_first(To[0], S2[m + 1]);
+    a = sqdiff2(To[1], S2[m + 2], a);
+    a = sqdiff2(To[2], S2[m + 3], a);
+    const float d0 = t0.x - S2[m].y;       // q = 0: partner bin c
+    const float d7 = t1.w - S2[m + 4].x;   // q = 7: partner bin c + 7
+    r[2 * m + 1] = fmaf(d0, d0, a.x) + fmaf(d7, d7, a.y);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) R.p[i] = make_float2(r[2 * i], r[2 * i + 1]);
+  R.s = r[8];
+}
+
+__device__ __forceinline__ RowT rowt_zero() {
+  RowT z;
+#pragma unroll
+  for (int i = 0; i < 4; i++) z.p[i] = make_float2(0.f, 0.f);
+  z.s = 0.f;
+  return z;
+}
+__device__ __forceinline__ RowT rowt_add(const RowT& a, const RowT& b) {
+  RowT o;
+#pragma unroll
+  for (int i = 0; i < 4; i++) o.p[i] = __fadd2_rn(a.p[i], b.p[i]);
+  o.s = a.s + b.s;
+  return o;
+}
+__device__ __forceinline__ void rowt_emit(const Lane3& L, int tau, int dti, const RowT& d, bool edge,
+                                          bool valid) {
+  const float dd[NC3] = {d.p[0].x, d.p[0].y, d.p[1].x, d.p[1].y, d.p[2].x, d.p[2].y, d.p[3].x, d.p[3].y,
+                         d.s};
+  emit_flags3(L, tau, dti, dd, edge, valid);
+}
+
+__device__ __forceinline__ void walk_plain3p(const Lane3& L, int dti, int ta, int tb, bool edge) {
+  const int dt = dti - kNlmPast;
+  RowT R1 = rowt_zero(), A[2], B[4];
+  A[0] = A[1] = R1;
+  B[0] = B[1] = B[2] = B[3] = R1;
+  const int steps = tb + 7;
+  for (int i0 = ta; i0 < steps; i0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u;
+      int ra = 12 + i;                             // tile row of frame t0 - 4 + i
+      ra = ra > ROWS3 - 1 ? ROWS3 - 1 : ra;
+      RowT R0;
+      rowterms3p(L, ra, ra + dt, R0);
+      const RowT a0 = rowt_add(R1, R0);
+      const RowT b0 = rowt_add(A[u & 1], a0);
+      const RowT d = rowt_add(B[u & 3], b0);
+      R1 = R0;
+      A[u & 1] = a0;
+      B[u & 3] = b0;
+      const int tau = i - 7;
+      rowt_emit(L, tau, dti, d, edge, tau >= ta && tau < tb);
+    }
+  }
+}
+
+__device__ __forceinline__ void walk_wrap3p(const Lane3& L, int dti, int ta, int tb, bool edge) {
+  const int dt = dti - kNlmPast;
+  int rlo = 0, rhi = 8, shift = 0;                   // rows r < rlo or r >= rhi use the alias
+  if (dt > 1) { rhi = 9 - dt; shift = -NDT; }        // dt = 2,3,4
+  else { rlo = -12 - dt; shift = NDT; }              // dt = -13..-16
+  RowT age[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) age[r] = rowt_zero();
+  const int steps = tb + 7;
+#pragma unroll 1
+  for (int i = ta; i < steps; i++) {
+    const int ra = 12 + i;
+    RowT Rm, Rw;
+    rowterms3p(L, ra, ra + dt, Rm);
+    rowterms3p(L, ra, ra + dt + shift, Rw);
+#pragma unroll
+    for (int r = 7; r >= 1; r--) {
+      const bool w = (r < rlo) || (r >= rhi);
+      RowT sel;
+#pragma unroll
+      for (int k = 0; k < 4; k++) sel.p[k] = make_float2(w ? Rw.p[k].x : Rm.p[k].x, w ? Rw.p[k].y : Rm.p[k].y);
+      sel.s = w ? Rw.s : Rm.s;
+      age[r] = rowt_add(age[r - 1], sel);
+    }
+    {
+      const bool w = 0 < rlo;
+#pragma unroll
+      for (int k = 0; k < 4; k++) age[0].p[k] = make_float2(w ? Rw.p[k].x : Rm.p[k].x, w ? Rw.p[k].y : Rm.p[k].y);
+      age[0].s = w ? Rw.s : Rm.s;
+    }
+    const int tau = i - 7;
+    if (tau >= ta) rowt_emit(L, tau, dti, age[7], edge, true);
+  }
+}
+
 // S rows are addressed relative to `first_target_row` (+ chunk-local target index); Wg / Fg are
 // the chunk's scratch: Wg[(target * nfull + block) * WPITCH3 + candidate], Fg[(target * nfull +
 // block) * FW3 + word].
+template <bool PK>
 __global__ void __launch_bounds__(NTH3, 1)
 nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
             int targets, int last_row, float h, float* __restrict__ Wg, unsigned* __restrict__ Fg) {
@@ -362,8 +522,13 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
       const int ta = half == 2 ? mid : 0;
       const int tb = half == 1 ? mid : nT;
       if (ta >= tb) continue;
-      if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
-      else walk_plain3(L, dti, ta, tb, edge);
+      if (PK) {
+        if (dti < 4 || dti > 17) walk_wrap3p(L, dti, ta, tb, edge);
+        else walk_plain3p(L, dti, ta, tb, edge);
+      } else {
+        if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
+        else walk_plain3(L, dti, ta, tb, edge);
+      }
     }
   }
   __syncthreads();
@@ -434,6 +599,110 @@ nlm3_paste_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int
   out[(size_t)tau * pitchO + bs + j] = res;
 }
 
+
+// Pass 2, second form: 8 lanes per (target, block), lanes over CANDIDATES.  Lane j takes the
+// accepted candidates of rank j, j + 8, ... (rank = position among the set bits of the field,
+// i.e. ascending (dt, df), the self candidate included), requests its weight and its eight
+// pasted values TOGETHER -- 72 loads in flight per pair and round instead of one L2 / DRAM
+// round trip per candidate -- and accumulates eight bin sums; the eight lanes are then added
+// by a transposing butterfly (7 shuffles) that leaves bin j in lane j.  The summation order
+// (per lane by rank, then a fixed tree over lanes) depends only on the pair's own candidate
+// set: deterministic and independent of the tiling, like the first form.
+__device__ __forceinline__ int nth_set_bit(unsigned v, int n) {   // position of the n-th (0-based) set bit
+  int pos = 0, c;
+  c = __popc(v & 0xffffu); if (n >= c) { n -= c; pos += 16; v >>= 16; }
+  c = __popc(v & 0xffu);   if (n >= c) { n -= c; pos += 8;  v >>= 8; }
+  c = __popc(v & 0xfu);    if (n >= c) { n -= c; pos += 4;  v >>= 4; }
+  c = __popc(v & 0x3u);    if (n >= c) { n -= c; pos += 2;  v >>= 2; }
+  if (n >= (int)(v & 1u)) pos += 1;
+  return pos;
+}
+
+__global__ void __launch_bounds__(128)
+nlm3_paste2_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
+                   int targets, const float* __restrict__ Wg, const unsigned* __restrict__ Fg,
+                   float* __restrict__ out, int pitchO) {
+  const int pair = blockIdx.x * 16 + (threadIdx.x >> 3);
+  const int j = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);          // the 8 lanes of this pair
+  if (pair >= targets * nfull) return;                          // whole groups leave together
+  const int tau = pair / nfull;
+  const int b = pair - tau * nfull;
+  const int bs = 8 * b;
+  const float* trow = S + (size_t)(first_target_row + tau) * pitchS;      // frame t
+  const float tv = trow[bs + j];
+  const uint4* fp = reinterpret_cast<const uint4*>(Fg + (size_t)pair * FW3);
+  const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1), f2 = __ldg(fp + 2);
+  unsigned fw[FW3] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+  float res = tv;
+  if (!((fw[GATED3 >> 5] >> (GATED3 & 31)) & 1u)) {
+    constexpr int kSelf = kNlmPast * 17 + kNlmRangeFreq;        // (dt 0, df 0): always accepted
+    fw[GATED3 >> 5] &= ~(1u << (GATED3 & 31));
+    fw[kSelf >> 5] |= 1u << (kSelf & 31);
+    int cum[FW3 + 1];
+    cum[0] = 0;
+#pragma unroll
+    for (int i = 0; i < FW3; i++) cum[i + 1] = cum[i] + __popc(fw[i]);
+    const int n = cum[FW3];
+    const float w_self = schraudolph_exp3(-0.0f);
+    const float* wp = Wg + (size_t)pair * WPITCH3;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    float ws = 0.f;
+    for (int r0 = 0; r0 < n; r0 += 8) {
+      const int rank = r0 + j;
+      if (rank < n) {
+        unsigned word = fw[0];
+        int base = 0, wi = 0;
+#pragma unroll
+        for (int i = 1; i < FW3; i++)
+          if (rank >= cum[i]) { word = fw[i]; base = cum[i]; wi = i; }
+        const int p = 32 * wi + nth_set_bit(word, rank - base);   // candidate index dti * 17 + dfi
+        const int dti = (p * 241) >> 12;                          // p / 17 for p < 357
+        const int df = p - 17 * dti - kNlmRangeFreq;
+        const float* prow = trow + (ptrdiff_t)(dti - kNlmPast) * pitchS;   // frame t + dt
+        float wgt = (p == kSelf) ? w_self : __ldg(wp + p);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          int c = bs + i + df;                                    // bin clamp(bs + i + df)
+          c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
+          v[i] = __ldg(prow + c);
+        }
+        if (wgt < kNlmMinWeight) wgt = 0.f;                       // nlm_filter_avx.c:219-221
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fmaf(wgt, v[i], acc[i]);
+        ws += wgt;
+      }
+    }
+    // transposing butterfly over the 8 lanes of the pair: lane j ends with bin j
+    float a4[4], a2[2], a1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float send = (j & 4) ? acc[i] : acc[i + 4];
+      const float keep = (j & 4) ? acc[i + 4] : acc[i];
+      a4[i] = keep + __shfl_xor_sync(gmask, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const float send = (j & 2) ? a4[i] : a4[i + 2];
+      const float keep = (j & 2) ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(gmask, send, 2);
+    }
+    {
+      const float send = (j & 1) ? a2[0] : a2[1];
+      const float keep = (j & 1) ? a2[1] : a2[0];
+      a1 = keep + __shfl_xor_sync(gmask, send, 1);
+    }
+    ws += __shfl_xor_sync(gmask, ws, 4);
+    ws += __shfl_xor_sync(gmask, ws, 2);
+    ws += __shfl_xor_sync(gmask, ws, 1);
+    res = (ws > kNlmMinWeight) ? a1 / ws : tv;                    // nlm_filter_avx.c:237-243
+  }
+  out[(size_t)tau * pitchO + bs + j] = res;
+}
+
 }  // namespace
 
 // Targets per chunk: close to CHUNK3, and such that the grid of the distance kernel (target tiles
@@ -470,9 +739,21 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   const int nfull = g.K / 8;
   if (nfull <= 0 || targets <= 0) return true;
   // per device and context, hence on every call rather than once per process
-  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // measurement knob: SB_NLM_PACKED=0 selects the scalar FADD / FFMA row walk
+  static const bool packed = [] {
+    const char* e = getenv("SB_NLM_PACKED");
+    return e ? atoi(e) != 0 : true;
+  }();
+  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)SMEM3));
+  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)SMEM3));
   const int chunk = nlm3_chunk_targets(g.K);
+  // measurement knob: SB_NLM_PASTE=1 selects the first paste form (lanes over bins)
+  static const int paste_form = [] {
+    const char* e = getenv("SB_NLM_PASTE");
+    return e ? atoi(e) : 2;
+  }();
   Scratch3 sc;
   {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
@@ -495,16 +776,25 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   for (int t0 = 0; t0 < targets; t0 += chunk) {
     const int cnt = targets - t0 < chunk ? targets - t0 : chunk;
     dim3 grid((cnt + TT3 - 1) / TT3, (nfull + NB3 - 1) / NB3);
-    nlm3_kernel<<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
-                                           last_row, h, sc.W, sc.F);
+    if (packed)
+      nlm3_kernel<true><<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
+                                                   last_row, h, sc.W, sc.F);
+    else
+      nlm3_kernel<false><<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
+                                                    last_row, h, sc.W, sc.F);
     SB_LAUNCH_CHECK();
     const int pairs = cnt * nfull;
     // (paste on a side stream under the next chunk's distance kernel, two scratch sets: the NLM
     // launch alone 3.5 % faster, the two-lane step unchanged -- the other lane already fills
     // the ramps -- so the scratch stays single)
-    nlm3_paste_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
-                                                         first_target_row + t0, cnt, h, sc.W, sc.F,
-                                                         Shat + (size_t)t0 * g.Kp, g.Kp);
+    if (paste_form == 1)
+      nlm3_paste_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
+                                                           first_target_row + t0, cnt, h, sc.W, sc.F,
+                                                           Shat + (size_t)t0 * g.Kp, g.Kp);
+    else
+      nlm3_paste2_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
+                                                            first_target_row + t0, cnt, sc.W, sc.F,
+                                                            Shat + (size_t)t0 * g.Kp, g.Kp);
     SB_LAUNCH_CHECK();
   }
   return true;

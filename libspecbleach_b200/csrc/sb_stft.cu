@@ -170,7 +170,6 @@ __device__ __forceinline__ void pass_radix3(const float2* __restrict__ x, float2
 
 template <bool INV>
 __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
-  const int M = g.M;
   const float2* __restrict__ tw = g.tw;
   for (int f = 0; f < g.nfac; f++) {
     const int r = g.fac[f];
@@ -193,35 +192,61 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
       if (last) pass_radix3<INV, true>(x, y, tw, nbf, s, tstep, smagic);
       else pass_radix3<INV, false>(x, y, tw, nbf, s, tstep, smagic);
     } else {
-      // generic radix: one work item per output point; the r-term sum runs in
-      // double with double roots of unity and is rounded to float once
-      // consecutive threads take consecutive butterflies of the SAME output index t, so a warp
-      // needs only a few distinct roots per term (the root loads were the bottleneck of the
-      // radix-167 pass of N = 3006 when every lane asked for a different one)
+      // generic (odd prime) radix, in double with double roots of unity, rounded to float once.
+      // A work item is a butterfly and a PAIR of outputs t, r - t: with S_u = x_u + x_{r-u},
+      // D_u = x_u - x_{r-u} (u = 1 .. (r-1)/2) and w = root^(u t),
+      //   y_t     = x_0 + sum_u (S_u Re w + i D_u Im w),   y_{r-t} = x_0 + sum_u (S_u Re w - i D_u Im w)
+      // share their four real sums: (r-1)^2 real multiplies per butterfly instead of 4 r (r-1)
+      // (the radix-167 pass of N = 3006 was half the time of the whole adaptive 44.1 kHz path).
+      // Consecutive threads take consecutive butterflies of the SAME t, so a warp needs only a
+      // few distinct roots per term.
       const double2* __restrict__ root = g.twg + g.twg_off[f];
       const unsigned nbfmagic = g.pass_nbfmagic[f];
-      for (int item = threadIdx.x; item < M; item += blockDim.x) {
-        const int t = nbf == 1 ? item : (int)__umulhi((unsigned)item, nbfmagic);   // output index
+      const int half = (r - 1) >> 1;
+      const int items = nbf * (half + 1);
+      for (int item = threadIdx.x; item < items; item += blockDim.x) {
+        const int t = nbf == 1 ? item : (int)__umulhi((unsigned)item, nbfmagic);   // 0 .. half
         const int idx = item - t * nbf;                           // butterfly
         const int j = s == 1 ? idx : (int)__umulhi((unsigned)idx, smagic);
         const int q = idx - j * s;
-        const float2 v0 = x[q + s * j];
-        double ar = (double)v0.x, ai = (double)v0.y;
-        int ut = 0;
-        for (int u = 1; u < r; u++) {
-          ut += t;
-          if (ut >= r) ut -= r;
-          double2 w = root[ut];
-          if (INV) w.y = -w.y;
-          const float2 v = x[q + s * (j + u * l)];
-          ar = fma((double)v.x, w.x, fma(-(double)v.y, w.y, ar));
-          ai = fma((double)v.x, w.y, fma((double)v.y, w.x, ai));
+        const float2* xb = x + q + s * j;
+        const float2 v0 = xb[0];
+        if (t == 0) {
+          double ar = (double)v0.x, ai = (double)v0.y;
+          for (int u = 1; u < r; u++) {
+            const float2 v = xb[s * u * l];
+            ar += (double)v.x;
+            ai += (double)v.y;
+          }
+          y[q + s * (r * j)] = make_float2((float)ar, (float)ai);
+        } else {
+          double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+          int ut = 0;
+          for (int u = 1; u <= half; u++) {
+            ut += t;
+            if (ut >= r) ut -= r;
+            double2 w = root[ut];
+            if (INV) w.y = -w.y;
+            const float2 va = xb[s * u * l];
+            const float2 vb = xb[s * (r - u) * l];
+            const double sx = (double)va.x + (double)vb.x, sy = (double)va.y + (double)vb.y;
+            const double dx = (double)va.x - (double)vb.x, dy = (double)va.y - (double)vb.y;
+            p1 = fma(sx, w.x, p1);
+            p2 = fma(dy, w.y, p2);
+            p3 = fma(sy, w.x, p3);
+            p4 = fma(dx, w.y, p4);
+          }
+          const double ar = (double)v0.x + p1, ai = (double)v0.y + p3;
+          const double y1r = ar - p2, y1i = ai + p4;              // output t
+          const double y2r = ar + p2, y2i = ai - p4;              // output r - t
+          float2 w1 = __ldg(&tw[j * t * tstep]);
+          float2 w2 = __ldg(&tw[j * (r - t) * tstep]);
+          if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
+          y[q + s * (r * j + t)] = make_float2((float)(y1r * (double)w1.x - y1i * (double)w1.y),
+                                               (float)(y1r * (double)w1.y + y1i * (double)w1.x));
+          y[q + s * (r * j + r - t)] = make_float2((float)(y2r * (double)w2.x - y2i * (double)w2.y),
+                                                   (float)(y2r * (double)w2.y + y2i * (double)w2.x));
         }
-        float2 wo = __ldg(&tw[j * t * tstep]);
-        if (INV) wo.y = -wo.y;
-        const double yr = ar * (double)wo.x - ai * (double)wo.y;
-        const double yi = ar * (double)wo.y + ai * (double)wo.x;
-        y[q + s * (r * j + t)] = make_float2((float)yr, (float)yi);
       }
     }
     __syncthreads();

@@ -267,6 +267,7 @@ def test_config1_speech_wav_demo_flow(gpu, ref, tmp_path):
     out = tmp_path / "speech_denoised.wav"
     cmd = [str(tool), "--1d", "--frame-size", "50", "--learn-samples", str(learn), "--reduction", "20",
            "--whitening", "50", "--smoothing", "0", "--masking", "0.5", "--aggressiveness", "1.0",
+           "--strength", "0", "--tonal", "0",      # the demo leaves suppression_strength / tonal_reduction at 0
            str(wav), str(out)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr

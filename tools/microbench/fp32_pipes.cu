@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
       for (int i = 0; i < NV; i++) v[i] = v[i] + ra;
     } else if (MODE == 3) {     // the row-term pattern: d = t - s; r = fma(d, d, r)
 #pragma unroll
-      for (int i = 0; i < NV; i++) { const float d = ra - s[i]; v[i] = fmaf(d, d, v[i]); }
+      for (int i = 0; i < NV; i++) { const float d = ra - v[(i + 5) % NV]; s[i] = fmaf(d, d, s[i]); }   // not loop-invariant
     } else if (MODE == 4) {     // packed: FFMA2 three-register
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
@@ -39,13 +39,31 @@ __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
     } else if (MODE == 5) {     // packed row-term pattern: d2 = t2 - s2 (FADD2 with negated operand), r2 = fma2(d2, d2, r2)
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
-        const float2 d = __fadd2_rn(make_float2(ra, rb), make_float2(-s[i], -s[i + 1]));
-        float2 x = __ffma2_rn(d, d, make_float2(v[i], v[i + 1]));
-        v[i] = x.x; v[i + 1] = x.y;
+        const int j = (i + 6) % NV;
+        const float2 d = __fadd2_rn(make_float2(ra, rb), make_float2(-v[j], -v[j + 1]));
+        float2 x = __ffma2_rn(d, d, make_float2(s[i], s[i + 1]));
+        s[i] = x.x; s[i + 1] = x.y;
       }
     } else if (MODE == 6) {     // FMNMX (alu pipe) interleaved with FFMA: do they co-issue?
 #pragma unroll
       for (int i = 0; i < NV; i += 2) { v[i] = fmaf(v[i], ra, rb); v[i + 1] = fminf(v[i + 1], s[i]); s[i] += 1.0f; }
+    } else if (MODE == 8) {     // FFMA2 + FMNMX 1:1 -- does the ALU instruction issue under the 2-cycle FFMA2?
+#pragma unroll
+      for (int i = 0; i < NV; i += 2) {
+        float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), make_float2(ra, rb), make_float2(rb, ra));
+        v[i] = x.x; v[i + 1] = x.y;
+        s[i] = fminf(s[i], x.x + 0.f * s[i + 1]) ; s[i + 1] = fmaxf(s[i + 1], ra);
+      }
+    } else if (MODE == 9) {     // FFMA + FMNMX 1:1
+#pragma unroll
+      for (int i = 0; i < NV; i++) { v[i] = fmaf(v[i], ra, rb); s[i] = fminf(s[i], v[(i + 3) % NV]); }
+    } else if (MODE == 10) {    // FFMA2 + 2 FMNMX per FFMA2 (same useful work as mode 9)
+#pragma unroll
+      for (int i = 0; i < NV; i += 2) {
+        float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), make_float2(ra, rb), make_float2(rb, ra));
+        v[i] = x.x; v[i + 1] = x.y;
+        s[i] = fminf(s[i], v[(i + 3) % NV]); s[i + 1] = fminf(s[i + 1], v[(i + 4) % NV]);
+      }
     } else if (MODE == 7) {     // FADD2 alone
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
@@ -92,6 +110,8 @@ int main() {
   run<5>("FADD2 + FFMA2(d,d,r) [packed row term]", 3, 1);
   run<6>("FFMA + FMNMX + FADD interleaved", 2, 1.5);
   run<7>("FADD2 reg pairs", 1, 0.5);
+  run<9>("FFMA + FMNMX 1:1", 2, 2);
+  run<10>("FFMA2 + 2 FMNMX (same work as above)", 2, 1.5);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
