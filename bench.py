@@ -661,6 +661,103 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------
+# N3: one file, time tiles over several GPUs of ONE process (strong scaling)
+# ---------------------------------------------------------------------------
+def run_tiled(args):
+    import torch
+    import libspecbleach_b200 as sb
+    from libspecbleach_b200 import api
+    if args.config != 2 or "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        raise SystemExit("bench.py --tiled: config 2, one process (no torchrun); --gpus N selects the devices")
+    if not torch.cuda.is_available() or torch.cuda.device_count() < args.gpus:
+        raise SystemExit("bench.py --tiled: not enough CUDA devices -- the product path has no CPU fallback")
+    w = Workload(2, 1, 0)
+    devices = list(range(args.gpus))
+    sb.set_device(0)
+    torch.cuda.set_device(0)
+    L = api.lib()
+    lanes = args.lanes or 4
+    if not L.specbleach_b200_configure(args.chunk_frames or 0, lanes):
+        raise SystemExit("bench.py: specbleach_b200_configure failed: " + sb.last_error())
+    tiles = args.tiles or lanes * args.gpus
+    uniq = w.make_unique_streams()
+    n, n_learn = w.n, w.n_learn
+    den = [sb.Denoiser2D(w.sr, w.frame_ms) for _ in range(2)]
+    x_pin = [api.PinnedArray(n) for _ in range(2)]
+    y_pin = [api.PinnedArray(n) for _ in range(2)]
+    for p, c in zip(x_pin, uniq):
+        p.array[:] = c
+
+    def step(tiled: bool):
+        for d in den:
+            d.reset_profile()
+            d.load_parameters(learn_noise=1)
+        if not sb.process_batch(den, [p.array[:n_learn] for p in x_pin], [p.array[:n_learn] for p in y_pin]):
+            raise RuntimeError(sb.last_error())
+        for c, d in enumerate(den):
+            d.load_parameters(**w.params[c])
+        if tiled:
+            for c, d in enumerate(den):
+                d.process_tiled(x_pin[c].array[n_learn:], tiles, args.warmup_frames, devices,
+                                out=y_pin[c].array[n_learn:])
+        elif not sb.process_batch(den, [p.array[n_learn:] for p in x_pin], [p.array[n_learn:] for p in y_pin]):
+            raise RuntimeError(sb.last_error())
+
+    def sync_all():
+        for d in devices:
+            torch.cuda.synchronize(d)
+
+    def timed(tiled: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            step(tiled)
+        sync_all()
+        L.specbleach_b200_stats_reset()
+        samplers = [ClockSampler(d) for d in devices]
+        for sm in samplers:
+            sm.start()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(tiled)
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3
+        clocks = [sm.stop() for sm in samplers]
+        return wall, clocks, api.stats()
+
+    # untiled run first (one GPU, the e2e path of the default bench): reference output + v_1
+    ms_1, _, _ = timed(False, args.steps, args.warmup)
+    ref_out = [p.array.copy() for p in y_pin]
+    ms_t, clocks, st = timed(True, args.steps, args.warmup)
+    same = all(np.array_equal(a, p.array) for a, p in zip(ref_out, y_pin))
+    maxdiff = max(float(np.max(np.abs(a - p.array))) for a, p in zip(ref_out, y_pin))
+    audio = w.seconds * args.steps
+    v1 = audio / (ms_1 / 1e3)
+    vt = audio / (ms_t / 1e3)
+    line = {
+        "metric": w.metric + " -- ONE file time-tiled over the GPUs (N3)", "value": vt, "unit": "x realtime",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_t / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(w.config_dict(), workload=w.what.replace("(one file per GPU)", "(ONE file for all GPUs)"),
+                       gpus=args.gpus, tiles_per_channel=tiles, warmup_frames=args.warmup_frames, lanes_per_gpu=lanes,
+                       timing="wall clock of the single driving process around synchronous "
+                              "specbleach_b200_process_tiled calls, every device synchronised on both sides "
+                              "(CUDA events do not span devices)"),
+        "e2e": {"value": vt, "unit": "x realtime", "h2d_bytes_per_step": 2 * n * 4, "d2h_bytes_per_step": 2 * n * 4,
+                "ms_per_step": ms_t / args.steps,
+                "api": "specbleach_b200_process_tiled per channel (page-locked host buffers, tiles dealt to the "
+                       "lanes of every GPU), learn phase through specbleach_b200_process_batch"},
+        "untiled_one_gpu": {"value": v1, "ms_per_step": ms_1 / args.steps,
+                            "api": "specbleach_b200_process_batch, same host buffers, device 0"},
+        "speedup_over_untiled_one_gpu": vt / v1,
+        "strong_scaling_efficiency": vt / (v1 * args.gpus),
+        "bit_identical_to_untiled": same, "max_abs_diff_to_untiled": maxdiff,
+        "gpu_launches": int(st["kernel_launches"]),
+        "collective": "none: every tile reads its slice of the input and writes its slice of the output",
+        "clocks": clocks[0], "clocks_all_gpus": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -672,11 +769,19 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=11.0,
                     help="audio seconds per CPU worker per step in the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tiled", action="store_true",
+                    help="config 2 only: ONE 10-min stereo file, each channel cut into time tiles "
+                         "(specbleach_b200_process_tiled) over the lanes of --gpus GPUs driven by this one "
+                         "process (strong scaling; run WITHOUT torchrun)")
+    ap.add_argument("--tiles", type=int, default=0, help="time tiles per channel (0 = one per lane and GPU)")
+    ap.add_argument("--warmup-frames", type=int, default=512)
     ap.add_argument("--lanes", type=int, default=0, help="engine lanes (0 = library default)")
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per sub-call (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.tiled:
+        run_tiled(args)
     else:
         run_ours(args)
 

@@ -30,7 +30,11 @@ bool specbleach_b200_set_device(int device);
 /* Last error message of this library (empty string if none). */
 const char* specbleach_b200_last_error(void);
 
-/* Page-locked host buffers: process() detects them and DMA-copies directly. */
+/* Page-locked host buffers.  specbleach[_2d]_process and the batch call accept any host
+ * memory: page-locked buffers (these, or cudaHostAlloc / cudaHostRegister'ed memory) are
+ * DMA-copied directly under the kernels of the neighbouring sub-calls; pageable buffers
+ * (malloc, the stack) of large calls are staged by the calling thread through two page-locked
+ * bounce buffers of the lane, piece by piece, also under the kernels. */
 void* specbleach_b200_host_alloc(size_t bytes);
 void specbleach_b200_host_free(void* p);
 
@@ -61,6 +65,40 @@ bool specbleach_b200_process_batch_device(SpectralBleachHandle* instances, uint3
                                           const uint32_t* number_of_samples,
                                           const float* const* d_inputs,
                                           float* const* d_outputs);
+
+/* Time-tiled processing of ONE long stream: same contract as
+ * specbleach[_2d]_process on HOST buffers, but the `number_of_samples` are cut into `tiles`
+ * hop-aligned time tiles that run concurrently on the engine's lanes and, when `devices` names
+ * more GPUs of this process, on those as well (no data-path collective: every tile reads its
+ * slice of `input` and writes its slice of `output`).  Tile 0 continues the handle; every other
+ * tile runs on a fresh internal handle that received the finalised noise profile and the
+ * parameters and starts `warmup_frames` hops early (its warm-up output is dropped); afterwards
+ * the handle continues from the state of the last tile.  The handle must be in denoise mode.
+ * Manual-profile mode: with warmup_frames >= 512 the output equals specbleach[_2d]_process bit
+ * for bit in the tests (the carried recursions decay by >= 0.09 per frame).  Adaptive estimators
+ * are only approximated (long memories): refused unless `flags` has
+ * SPECBLEACH_B200_TILED_ALLOW_ADAPTIVE.  Pageable buffers are page-locked for the call. */
+enum { SPECBLEACH_B200_TILED_ALLOW_ADAPTIVE = 1 };
+bool specbleach_b200_process_tiled(SpectralBleachHandle instance, uint32_t number_of_samples,
+                                   const float* input, float* output, uint32_t tiles,
+                                   uint32_t warmup_frames, const int* devices,
+                                   uint32_t device_count, uint32_t flags);
+
+/* Strategy branches of the reference that its shipped build never selects.  The
+ * reference fixes them at compile time: GAIN_ESTIMATION_TYPE_1D / _2D (configurations.h:195,218),
+ * the SuppressionType literal in spectral_denoiser.c:294-297 / spectral_2d_denoiser.c:397-400 and
+ * the TimeSmoothingType literal in spectral_denoiser.c:83.  Here they are per-handle settings
+ * with the reference's enum values; the defaults are the shipped build's (WIENER, BEROUTI_PER_BIN,
+ * FIXED), so a handle that never calls this is the drop-in path.  Parity is held against
+ * rebuilds of the reference with the selector pinned (oracle/variants/).
+ *   gain_type        0 WIENER, 1 GATES, 2 GENERALIZED_SPECTRALSUBTRACTION   (gain_calculator.c:71-139)
+ *   suppression_type 0 BEROUTI_PER_BIN, 1 GLOBAL_SNR, 2 CRITICAL_BANDS_SNR, 3 MASKING_THRESHOLDS,
+ *                    4 NONE                                               (suppression_engine.c:135-275)
+ *   smoothing_type   1 FIXED, 2 TRANSIENT_AWARE (1D denoiser only; ignored by the 2D denoiser,
+ *                    which has no temporal smoother)    (spectral_smoother.c:141-181, transient_detector.c:66-111)
+ * May be changed between any two process() calls, like the parameters. */
+bool specbleach_b200_set_strategy(SpectralBleachHandle instance, int gain_type, int suppression_type,
+                                  int smoothing_type);
 
 /* Noise-profile persistence ------------------------------------------------
  * The reference can only hand out / take in raw profile arrays

@@ -65,7 +65,7 @@ EXTENSION_SYMBOLS = ["specbleach_b200_" + n for n in (
     "process_device", "process_batch", "process_batch_device", "profile", "stats_reset",
     "stats_get", "stats_classes", "stats_class_name", "stats_class", "get_geometry",
     "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft", "profile_save", "profile_load",
-    "state_size", "state_save", "state_load", "process_interleaved")]
+    "state_size", "state_save", "state_load", "process_interleaved", "process_tiled", "set_strategy")]
 
 
 def lib():
@@ -143,6 +143,11 @@ def lib():
     L.specbleach_b200_process_interleaved.restype = C.c_bool
     L.specbleach_b200_process_interleaved.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32,
                                                       C.c_int, C.c_void_p, C.c_void_p]
+    L.specbleach_b200_process_tiled.restype = C.c_bool
+    L.specbleach_b200_process_tiled.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.c_uint32]
+    L.specbleach_b200_set_strategy.restype = C.c_bool
+    L.specbleach_b200_set_strategy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.specbleach_b200_get_geometry.restype = C.c_bool
     L.specbleach_b200_get_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
     L.specbleach_b200_debug_fp32_peak_tflops.restype = C.c_double
@@ -295,6 +300,22 @@ class Denoiser:
 
     def load_state(self, blob: bytes) -> bool:
         return bool(self.L.specbleach_b200_state_load(self.h, blob, len(blob)))
+
+    def process_tiled(self, x: np.ndarray, tiles: int, warmup_frames: int = 512, devices=None,
+                      allow_adaptive: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """specbleach_b200_process_tiled: one call over ``x`` cut into ``tiles`` time tiles."""
+        x = np.ascontiguousarray(x, dtype=np.float32) if not isinstance(x, np.ndarray) or x.dtype != np.float32 else x
+        y = np.empty_like(x) if out is None else out
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        if not self.L.specbleach_b200_process_tiled(self.h, x.shape[0], x.ctypes.data, y.ctypes.data, int(tiles),
+                                                    int(warmup_frames), devs, len(devices) if devices else 0,
+                                                    1 if allow_adaptive else 0):
+            raise RuntimeError("process_tiled failed: " + last_error())
+        return y
+
+    def set_strategy(self, gain_type: int = 0, suppression_type: int = 0, smoothing_type: int = 1) -> bool:
+        """specbleach_b200_set_strategy: the reference's compile-time strategy selectors (N4)."""
+        return bool(self.L.specbleach_b200_set_strategy(self.h, gain_type, suppression_type, smoothing_type))
 
     def geometry(self) -> dict:
         v = [C.c_uint32() for _ in range(4)]

@@ -227,6 +227,30 @@ bool specbleach_b200_process_batch_device(SpectralBleachHandle* instances, uint3
                            true);
 }
 
+bool specbleach_b200_process_tiled(SpectralBleachHandle instance, uint32_t n, const float* input,
+                                   float* output, uint32_t tiles, uint32_t warmup_frames,
+                                   const int* devices, uint32_t device_count, uint32_t flags) {
+  if (!instance || n == 0 || !input || !output) return false;
+  return sb::process_tiled(H(instance), n, input, output, tiles, warmup_frames, devices, device_count,
+                           flags);
+}
+
+bool specbleach_b200_set_strategy(SpectralBleachHandle instance, int gain_type, int suppression_type,
+                                  int smoothing_type) {
+  if (!instance) return false;
+  if (gain_type < 0 || gain_type > 2 || suppression_type < 0 || suppression_type > 4 ||
+      smoothing_type < 1 || smoothing_type > 2) {
+    sb::set_error_msg("specbleach_b200_set_strategy: gain 0..2, suppression 0..4, smoothing 1..2");
+    return false;
+  }
+  std::lock_guard<std::recursive_mutex> engine_lock(sb::engine_mutex());
+  Handle* h = H(instance);
+  h->gain_type = gain_type;
+  h->suppression_type = suppression_type;
+  h->smoothing_type = smoothing_type;
+  return true;
+}
+
 void specbleach_b200_profile(int enable) { sb::g_profile = enable != 0; }
 void specbleach_b200_stats_reset(void) {
   sb::Context& c = sb::ctx();

@@ -58,6 +58,7 @@ constexpr int kOverlap = 4;                     // :182 / :204
 constexpr int kZeroPad = 800;                   // :188 / :210
 constexpr int kMaxBands = 25;                   // critical_bands.c:25-28
 constexpr int kBandPitch = 32;                  // pitch of per-band arrays
+constexpr int kBandStateRows = 5;               // Handle::d_band_state rows
 constexpr int kMaxBandTasks = 96;               // band-sum work units per frame
 
 constexpr int kDelayFrames = kNlmFuture;        // 2D look-ahead (nlm_filter.c:447-452)
@@ -151,6 +152,10 @@ struct Lane {
   cudaEvent_t ev_out[2] = {nullptr, nullptr};   // out_stage[b] written by the compute stream
   cudaEvent_t ev_done[2] = {nullptr, nullptr};  // D2H from out_stage[b] finished
   unsigned io_seq = 0;                          // host sub-calls enqueued on this lane
+  // page-locked bounce buffers for callers that pass pageable memory (allocated on first use)
+  float* pin_in[2] = {nullptr, nullptr};
+  float* pin_out[2] = {nullptr, nullptr};
+  size_t pin_cap = 0;
   std::vector<cudaEvent_t> ev; // profiling event pairs (NLM)
 };
 
@@ -209,7 +214,9 @@ struct Handle {
   // veto / smoothing recursions
   float* d_stable = nullptr;      // [Kp]
   float* d_sp_prev = nullptr;     // [Kp] 1D release smoother
-  float* d_band_state = nullptr;  // [2][32]: u = T_prev^0.6, protection memory
+  float* d_band_state = nullptr;  // [5][32]: u = T_prev^0.6, protection memory; N4: u of the suppression
+                                  // engine's masking estimator, transient detector energies, its flag
+  int gain_type = 0, suppression_type = 0, smoothing_type = 1;   // N4 strategy selectors (GainArgs)
   // static-noise caches: tonal mask and whitening weights of the manual profile
   float* d_aux_mask = nullptr;    // [Kp]
   float* d_aux_wt = nullptr;      // [Kp]
@@ -302,6 +309,11 @@ struct GainArgs {
   bool two_d;
   float strength, tonal, reduction, whitening, depth, smoothing;
   bool residual;
+  // N4: strategy branches the shipped reference build never selects (enum values of
+  // gain_calculator.h:27-31, suppression_engine.h:39-46, spectral_smoother.h:28-31)
+  int gain_type = 0;         // 0 Wiener, 1 gates, 2 generalized spectral subtraction
+  int suppression_type = 0;  // 0 Berouti per bin, 1 global SNR, 2 critical-band SNR, 3 masking thresholds, 4 none
+  int smoothing_type = 1;    // 1D: 1 fixed, 2 transient aware
   int mask_stride;   // 0: one tonal mask row shared by all frames, else Kp
   int wt_stride;     // 0: one whitening-weight row shared by all frames, else Kp
   const float* mask; // tonal mask rows (indexed by frame index * mask_stride)

@@ -10,6 +10,7 @@
 #include "sb_engine.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -43,7 +44,7 @@ const char* last_error() {
 // ---------------------------------------------------------------------------
 // Per-kernel-class timing
 // ---------------------------------------------------------------------------
-struct KEvent { int cls; cudaEvent_t e0, e1; };
+struct KEvent { int cls; cudaEvent_t e0, e1; cudaStream_t st; };
 static std::vector<KEvent> g_kevents;
 static std::mutex g_kev_mu;
 static const char* const kNames[kcCount] = {
@@ -54,6 +55,7 @@ const char* kclass_name(int c) { return (c >= 0 && c < kcCount) ? kNames[c] : "?
 void ktimer_begin(int cls, cudaStream_t st) {
   KEvent k;
   k.cls = cls;
+  k.st = st;
   if (cudaEventCreate(&k.e0) != cudaSuccess || cudaEventCreate(&k.e1) != cudaSuccess) return;
   cudaEventRecord(k.e0, st);
   std::lock_guard<std::mutex> lock(g_kev_mu);
@@ -199,7 +201,7 @@ Handle* handle_create(bool two_d, uint32_t sample_rate, float frame_ms) {
             dev_zalloc(&h->d_hist, (size_t)g.frame + g.hop) &&
             dev_zalloc(&h->d_tail[0], g.frame) && dev_zalloc(&h->d_tail[1], g.frame) &&
             dev_zalloc(&h->d_stable, Kp) && dev_zalloc(&h->d_sp_prev, Kp) &&
-            dev_zalloc(&h->d_band_state, 2 * kBandPitch) && dev_zalloc(&h->d_noise_cur, Kp) &&
+            dev_zalloc(&h->d_band_state, kBandStateRows * kBandPitch) && dev_zalloc(&h->d_noise_cur, Kp) &&
             dev_zalloc(&h->d_floor, Kp) && dev_zalloc(&h->d_aux_mask, Kp) &&
             dev_zalloc(&h->d_aux_wt, Kp);
   if (ok && two_d) {
@@ -333,6 +335,26 @@ bool sub_begin(Handle* h, Lane& L) {
   return d2d(L.xbuf, h->d_hist, hist_len(h), L.stream);
 }
 
+// learn -> denoise transition (denoiser_profile_core.c:42-48): every available profile is refined
+// once (gap interpolation + smoothing, noise_estimator.c:143-162) and the host mirror follows.
+static bool finalize_profiles(Handle* h, cudaStream_t st) {
+  if (!h->was_learning) return true;
+  const GeoK& g = h->geo->k;
+  if (h->host_dirty && !upload_profiles(h, st)) return false;
+  unsigned mask = 0;
+  for (int m = 0; m < 4; m++)
+    if (h->available[m]) mask |= 1u << m;
+  if (!launch_interp_smooth(g, h->d_prof, g.Kp, 4, mask, kInterpThreshold, kNoiseSmoothing,
+                            nullptr, st))
+    return false;
+  if (!download_profiles(h, st)) return false;
+  SB_CUDA(cudaStreamSynchronize(st));
+  refresh_profile_learned(h);
+  h->was_learning = false;
+  h->noise_version++;
+  return true;
+}
+
 static bool denoise_frames(Handle* h, Lane& L, int M) {
   const GeoK& g = h->geo->k;
   cudaStream_t st = L.stream;
@@ -342,20 +364,7 @@ static bool denoise_frames(Handle* h, Lane& L, int M) {
   const int lead = two_d ? kDelayFrames : 0;   // history rows in front of X / noise
 
   // -- learn -> denoise transition: refine every available profile once --
-  if (h->was_learning) {   // denoiser_profile_core.c:42-48
-    if (h->host_dirty && !upload_profiles(h, st)) return false;
-    unsigned mask = 0;
-    for (int m = 0; m < 4; m++)
-      if (h->available[m]) mask |= 1u << m;
-    if (!launch_interp_smooth(g, h->d_prof, g.Kp, 4, mask, kInterpThreshold, kNoiseSmoothing,
-                              nullptr, st))
-      return false;
-    if (!download_profiles(h, st)) return false;
-    SB_CUDA(cudaStreamSynchronize(st));
-    refresh_profile_learned(h);
-    h->was_learning = false;
-    h->noise_version++;
-  }
+  if (!finalize_profiles(h, st)) return false;
   if (h->host_dirty && !upload_profiles(h, st)) return false;
 
   // -- spectra of the new frames (rows lead.. of the delayed buffers) --
@@ -419,6 +428,9 @@ static bool denoise_frames(Handle* h, Lane& L, int M) {
   ga.depth = p.depth;
   ga.smoothing = p.smoothing;
   ga.residual = p.residual_listen;
+  ga.gain_type = h->gain_type;
+  ga.suppression_type = h->suppression_type;
+  ga.smoothing_type = h->smoothing_type;
   ga.mask_stride = 0;
   ga.wt_stride = 0;
   ga.mask = h->d_aux_mask;
@@ -548,6 +560,9 @@ uint32_t max_sub_samples(const Handle* h) {
 // ---------------------------------------------------------------------------
 // Whole-call drivers
 // ---------------------------------------------------------------------------
+// What kind of memory a caller's buffer is.  Device and page-locked host memory are DMA targets;
+// anything else (malloc, numpy, the stack) is pageable: cudaMemcpyAsync would stage it through
+// the driver's own bounce buffers synchronously, which serialises copies and kernels.
 static bool is_device_or_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -558,8 +573,103 @@ static bool is_device_or_pinned(const void* p) {
          a.type == cudaMemoryTypeManaged;
 }
 
-// Enqueues the whole call on the lane; does not synchronise.
-bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, bool device_io) {
+// One host sub-call on the lane's three-stream pipeline: H2D of `m` samples from the page-locked
+// `src` on the copy-in stream into staging buffer b (it may run while the kernels of the
+// previous sub-call are still busy), kernels on the lane stream, D2H to the page-locked `dst`
+// on the copy-out stream.  ev_in[b] = H2D done, ev_done[b] = D2H done.
+static bool enqueue_host_sub(Handle* h, Lane& L, uint32_t m, const float* src, float* dst, int* b_out,
+                             uint32_t skip = 0) {
+  if (!sub_begin(h, L)) return false;
+  float* x = L.xbuf + hist_len(h);
+  const int b = (int)(L.io_seq & 1u);
+  const bool reused = L.io_seq >= 2;
+  L.io_seq++;
+  if (reused) SB_CUDA(cudaStreamWaitEvent(L.s_in, L.ev_used[b], 0));
+  SB_CUDA(cudaMemcpyAsync(L.in_stage[b], src, m * sizeof(float), cudaMemcpyHostToDevice, L.s_in));
+  SB_CUDA(cudaEventRecord(L.ev_in[b], L.s_in));
+  SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_in[b], 0));
+  if (!d2d(x, L.in_stage[b], m, L.stream)) return false;
+  SB_CUDA(cudaEventRecord(L.ev_used[b], L.stream));
+  if (reused) SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_done[b], 0));
+  if (!sub_run(h, L, m, L.out_stage[b])) return false;
+  SB_CUDA(cudaEventRecord(L.ev_out[b], L.stream));
+  SB_CUDA(cudaStreamWaitEvent(L.s_out, L.ev_out[b], 0));
+  // `skip`: leading output samples nobody wants (warm-up of a time tile)
+  if (skip < m)
+    SB_CUDA(cudaMemcpyAsync(dst + skip, L.out_stage[b] + skip, (m - skip) * sizeof(float),
+                            cudaMemcpyDeviceToHost, L.s_out));
+  SB_CUDA(cudaEventRecord(L.ev_done[b], L.s_out));
+  *b_out = b;
+  return true;
+}
+
+// Pageable caller buffers (what a program written against the reference passes to
+// specbleach[_2d]_process: examples/denoiser_demo.c:217-300): the call is cut into sub-calls of a
+// quarter of the lane's capacity, each copied by THIS thread into one of two page-locked bounce
+// buffers of the lane and handed to the same pipeline; its output comes back through two more.
+// The host copies of sub-call k run while the GPU works on k-1, so the call costs
+// max(host copies, kernels) instead of their sum.  in == out is fine: output k-2 is written
+// behind the input position already consumed.
+static bool lane_ensure_bounce(Lane& L) {
+  if (L.pin_cap >= L.cap_samples && L.pin_in[0]) return true;
+  for (int b = 0; b < 2; b++) {
+    if (L.pin_in[b]) cudaFreeHost(L.pin_in[b]);
+    if (L.pin_out[b]) cudaFreeHost(L.pin_out[b]);
+    L.pin_in[b] = L.pin_out[b] = nullptr;
+  }
+  L.pin_cap = 0;
+  for (int b = 0; b < 2; b++) {
+    SB_CUDA(cudaMallocHost((void**)&L.pin_in[b], L.cap_samples * sizeof(float)));
+    SB_CUDA(cudaMallocHost((void**)&L.pin_out[b], L.cap_samples * sizeof(float)));
+  }
+  L.pin_cap = L.cap_samples;
+  return true;
+}
+
+static bool enqueue_call_pageable(Handle* h, Lane& L, uint32_t n, const float* in, float* out,
+                                  bool in_pageable, bool out_pageable) {
+  if (!lane_ensure_bounce(L)) return false;
+  const GeoK& gk = h->geo->k;
+  struct Pending { uint32_t pos = 0, m = 0; bool live = false; } pend[2];
+  uint32_t piece = (uint32_t)(sub_call_frames(gk) / 4 > 64 ? sub_call_frames(gk) / 4 : 64) * (uint32_t)gk.hop;
+  uint32_t pos = 0;
+  auto drain = [&](int b) -> bool {
+    if (!pend[b].live) return true;
+    SB_CUDA(cudaEventSynchronize(L.ev_done[b]));
+    if (out_pageable) memcpy(out + pend[b].pos, L.pin_out[b], (size_t)pend[b].m * sizeof(float));
+    pend[b].live = false;
+    return true;
+  };
+  while (pos < n) {
+    uint32_t m = n - pos;
+    const uint32_t cap = max_sub_samples(h);
+    if (m > piece) m = piece;
+    if (m > cap) m = cap;
+    const int b = (int)(L.io_seq & 1u);
+    // bounce buffer b: its previous H2D and D2H (sub-call k-2) must be over before it is reused
+    if (!drain(b)) return false;
+    if (L.io_seq >= 2) SB_CUDA(cudaEventSynchronize(L.ev_in[b]));
+    const float* src = in + pos;
+    if (in_pageable) {
+      memcpy(L.pin_in[b], in + pos, (size_t)m * sizeof(float));
+      src = L.pin_in[b];
+    }
+    float* dst = out_pageable ? L.pin_out[b] : out + pos;
+    int used = 0;
+    if (!enqueue_host_sub(h, L, m, src, dst, &used)) return false;
+    pend[used].pos = pos;
+    pend[used].m = m;
+    pend[used].live = true;
+    pos += m;
+  }
+  const int first = (int)(L.io_seq & 1u);       // the older of the two pending sub-calls
+  if (!drain(first) || !drain(first ^ 1)) return false;
+  return true;
+}
+
+// Enqueues the whole call on the lane; does not synchronise (device / page-locked buffers).
+bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, bool device_io,
+                  uint32_t skip_out = 0) {
   SB_CUDA(cudaSetDevice(h->device));
   uint32_t pos = 0;
   bool host_pending = false;
@@ -570,6 +680,12 @@ bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, b
   const GeoK& gk = h->geo->k;
   const uint32_t ramp = (uint32_t)(sub_call_frames(gk) / 8 > 64 ? sub_call_frames(gk) / 8 : 64) *
                         (uint32_t)gk.hop;
+  if (!device_io && n >= 2 * ramp && skip_out == 0) {
+    // large host call: pageable buffers go through the bounce pipeline (which synchronises
+    // itself); small calls are not worth two cudaPointerGetAttributes
+    const bool in_pg = !is_device_or_pinned(in), out_pg = !is_device_or_pinned(out);
+    if (in_pg || out_pg) return enqueue_call_pageable(h, L, n, in, out, in_pg, out_pg);
+  }
   while (pos < n) {
     uint32_t m = n - pos;
     const uint32_t cap = max_sub_samples(h);
@@ -578,34 +694,15 @@ bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, b
       else if (m <= cap && m > 2 * ramp) m -= ramp;
     }
     if (m > cap) m = cap;
-    if (!sub_begin(h, L)) return false;
-    float* dst = L.xbuf + hist_len(h);
     if (device_io) {
-      if (!d2d(dst, in + pos, m, L.stream)) return false;
+      if (!sub_begin(h, L)) return false;
+      if (!d2d(L.xbuf + hist_len(h), in + pos, m, L.stream)) return false;
       if (!sub_run(h, L, m, out + pos)) return false;
     } else {
-      // H2D on its own stream into a staging buffer (it may run while the kernels of the
-      // previous sub-call are still busy), kernels on the lane stream, D2H on a third stream
-      const int b = (int)(L.io_seq & 1u);
-      const bool reused = L.io_seq >= 2;
-      L.io_seq++;
-      if (reused) SB_CUDA(cudaStreamWaitEvent(L.s_in, L.ev_used[b], 0));
-      SB_CUDA(cudaMemcpyAsync(L.in_stage[b], in + pos, m * sizeof(float), cudaMemcpyHostToDevice,
-                              L.s_in));
-      SB_CUDA(cudaEventRecord(L.ev_in[b], L.s_in));
-      SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_in[b], 0));
-      if (!d2d(dst, L.in_stage[b], m, L.stream)) return false;
-      SB_CUDA(cudaEventRecord(L.ev_used[b], L.stream));
-      if (reused) SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_done[b], 0));
-      if (!sub_run(h, L, m, L.out_stage[b])) return false;
-      SB_CUDA(cudaEventRecord(L.ev_out[b], L.stream));
-      SB_CUDA(cudaStreamWaitEvent(L.s_out, L.ev_out[b], 0));
-      SB_CUDA(cudaMemcpyAsync(out + pos, L.out_stage[b], m * sizeof(float), cudaMemcpyDeviceToHost,
-                              L.s_out));
-      SB_CUDA(cudaEventRecord(L.ev_done[b], L.s_out));
+      const uint32_t sk = skip_out > pos ? (skip_out - pos < m ? skip_out - pos : m) : 0;
+      if (!enqueue_host_sub(h, L, m, in + pos, out + pos, &last_b, sk)) return false;
       // whoever synchronises the lane stream also waits for this copy
       host_pending = true;
-      last_b = b;
     }
     pos += m;
   }
@@ -613,7 +710,6 @@ bool enqueue_call(Handle* h, Lane& L, uint32_t n, const float* in, float* out, b
     // the D2H copies are ordered on s_out: waiting for the last one waits for all
     SB_CUDA(cudaStreamWaitEvent(L.stream, L.ev_done[last_b], 0));
   }
-  (void)is_device_or_pinned;
   return true;
 }
 
@@ -671,12 +767,238 @@ bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* 
   return ok;
 }
 
+// ---------------------------------------------------------------------------
+// N3: ONE long stream cut into time tiles that run on other lanes / GPUs.
+// ---------------------------------------------------------------------------
+// What a handle carries between frames forgets its start geometrically: the
+// 21-frame NLM ring and the 4-frame delay line are exact after 25 frames, the veto EMAs (0.5 per
+// frame) after ~150, the forward-masking recursion (<= 0.91 per frame at 48 kHz / 50 ms) after
+// ~400.  A tile therefore starts `warmup_frames` hops early on a FRESH handle that was given the
+// finalised noise profile and the parameters, and its warm-up output is dropped.  Tile 0
+// continues the caller's handle (exact); at the end the caller's handle takes over the state of
+// the last tile, so the stream can go on with ordinary process() calls.  Manual-profile mode:
+// with >= 512 warm-up frames the result equals the monolithic call bit for bit on every input
+// tried (tests/test_gpu_io.py).  Adaptive estimators have long memories (Martin: 96-frame minimum
+// history, Brandt: 150-frame window + hold) and are only approximated: opt-in by flag.
+// Tile handles are pooled per (device, geometry, denoiser kind): creating one costs 17 cudaMalloc
+// and destroying one as many device-synchronising cudaFree, far more than a tile's kernels.
+struct TilePoolKey {
+  int device;
+  const Geometry* geo;
+  bool two_d;
+  bool operator<(const TilePoolKey& o) const {
+    if (device != o.device) return device < o.device;
+    if (geo != o.geo) return geo < o.geo;
+    return two_d < o.two_d;
+  }
+};
+static std::map<TilePoolKey, std::vector<Handle*>> g_tile_pool;
+
+// back to the state of a freshly created handle (stream-ordered on `st`)
+static bool reset_stream_state(Handle* t, cudaStream_t st) {
+  const GeoK& g = t->geo->k;
+  const size_t Kp = g.Kp;
+  struct Z { float* p; size_t n; };
+  const Z z[] = {{t->d_med_ring, (size_t)kMedianFrames * Kp}, {t->d_hist, (size_t)g.frame + g.hop},
+                 {t->d_tail[0], (size_t)g.frame}, {t->d_tail[1], (size_t)g.frame}, {t->d_stable, Kp},
+                 {t->d_sp_prev, Kp}, {t->d_band_state, (size_t)kBandStateRows * kBandPitch}, {t->d_X_hist_re, 4 * Kp},
+                 {t->d_X_hist_im, 4 * Kp}, {t->d_noise_hist, 4 * Kp}, {t->d_S_hist, (size_t)kSnrHist * Kp}};
+  for (const Z& e : z)
+    if (e.p) SB_CUDA(cudaMemsetAsync(e.p, 0, e.n * sizeof(float), st));
+  t->med_write = 0;
+  t->tail_cur = 0;
+  t->carry = 0;
+  t->was_learning = false;
+  t->profile_dl_pending = false;
+  t->dn_frames = 0;
+  for (int r = 0; r < 4; r++) t->noise_hist_version[r] = 0;
+  t->aux_mask_version = t->aux_wt_version = 0;
+  t->aux_wt_whitening = -1.0f;
+  t->last_adaptive_state = 0;
+  t->params_loaded = false;
+  t->prm = Params();
+  if (t->d_est) {               // a fresh estimator of the next load_parameters
+    SB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(t->d_est);
+    t->d_est = nullptr;
+    t->est_floats = 0;
+  }
+  t->est_method = -1;
+  return true;
+}
+
+static Handle* clone_for_tile(const Handle* h, int device, cudaStream_t st_hint) {
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  const Geometry* geo = get_geometry(h->geo->sample_rate, h->geo->frame_ms);
+  Handle* t = nullptr;
+  if (geo) {
+    std::vector<Handle*>& pool = g_tile_pool[TilePoolKey{device, geo, h->two_d}];
+    if (!pool.empty()) {
+      t = pool.back();
+      pool.pop_back();
+      if (!reset_stream_state(t, st_hint)) {
+        handle_destroy(t);
+        t = nullptr;
+      }
+    }
+  }
+  if (!t) t = handle_create(h->two_d, h->geo->sample_rate, h->geo->frame_ms);
+  if (!t) return nullptr;
+  for (int m = 0; m < 4; m++) {
+    t->prof_host[m] = h->prof_host[m];
+    t->block_count[m] = h->block_count[m];
+    t->available[m] = h->available[m];
+  }
+  t->profile_learned = h->profile_learned;
+  t->host_dirty = true;
+  t->noise_version++;
+  t->nlm_h = h->nlm_h;
+  t->gain_type = h->gain_type;
+  t->suppression_type = h->suppression_type;
+  t->smoothing_type = h->smoothing_type;
+  if (h->params_loaded && !handle_load_parameters(t, h->prm)) {   // creates the estimator if adaptive
+    handle_destroy(t);
+    return nullptr;
+  }
+  t->nlm_h = h->nlm_h;
+  return t;
+}
+
+static void release_tile_handle(Handle* t) {
+  g_tile_pool[TilePoolKey{t->device, t->geo, t->two_d}].push_back(t);
+}
+
+bool process_tiled(Handle* h, uint32_t n, const float* in, float* out, uint32_t tiles,
+                   uint32_t warmup_frames, const int* devices, uint32_t device_count, uint32_t flags) {
+  std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
+  DeviceGuard restore_device;
+  if (h->prm.learn_noise > 0 || !h->params_loaded) {
+    set_error_msg("specbleach_b200_process_tiled: the handle must be in denoise mode (load_parameters with learn_noise = 0)");
+    return false;
+  }
+  if (h->prm.adaptive && !(flags & 1u)) {
+    set_error_msg("specbleach_b200_process_tiled: adaptive noise estimation is only approximated by time "
+                  "tiles; pass SPECBLEACH_B200_TILED_ALLOW_ADAPTIVE to accept that");
+    return false;
+  }
+  const GeoK& g = h->geo->k;
+  const uint32_t hop = (uint32_t)g.hop;
+  const uint32_t first = (hop - h->carry) % hop;          // first frame boundary of the stream inside this call
+  const uint32_t frames = n > first ? (n - first) / hop : 0;
+  if (tiles > frames / 64) tiles = frames / 64;           // tiles shorter than 64 frames are pointless
+  if (tiles <= 1) return process_call(h, n, in, out, false);
+  if ((in <= out && out < in + n) || (out <= in && in < out + n)) {
+    // a tile's warm-up input is the previous tile's output region: not in place
+    set_error_msg("specbleach_b200_process_tiled: input and output must not overlap");
+    return false;
+  }
+  SB_CUDA(cudaSetDevice(h->device));
+  Lane* L0 = get_lane(0, g);
+  if (!L0) return false;
+  if (!finalize_profiles(h, L0->stream)) return false;    // the clones take the refined profile
+  // page-locked buffers are DMA'd by every device; pageable ones are registered for the call
+  bool reg_in = false, reg_out = false;
+  if (!is_device_or_pinned(in)) {
+    if (cudaHostRegister(const_cast<float*>(in), (size_t)n * sizeof(float), cudaHostRegisterPortable) == cudaSuccess)
+      reg_in = true;
+    else cudaGetLastError();
+  }
+  if (out != in && !is_device_or_pinned(out)) {
+    if (cudaHostRegister(out, (size_t)n * sizeof(float), cudaHostRegisterPortable) == cudaSuccess) reg_out = true;
+    else cudaGetLastError();
+  }
+  struct Tile { uint32_t in_lo, out_lo, out_hi; Handle* h; int device; Lane* lane; };
+  std::vector<Tile> plan;
+  for (uint32_t i = 0; i < tiles; i++) {
+    const uint32_t base = frames / tiles, extra = frames % tiles;
+    const uint32_t lo_f = i * base + (i < extra ? i : extra);
+    const uint32_t hi_f = lo_f + base + (i < extra ? 1u : 0u);
+    Tile t;
+    t.out_lo = i == 0 ? 0u : first + lo_f * hop;
+    t.out_hi = i == tiles - 1 ? n : first + hi_f * hop;
+    t.in_lo = t.out_lo;
+    t.h = nullptr;
+    t.device = h->device;
+    t.lane = nullptr;
+    if (i > 0) {
+      const uint64_t back = (uint64_t)warmup_frames * hop;
+      if ((uint64_t)(t.out_lo - first) < back) {
+        // its warm-up would reach before the call: tile 0 (the exact continuation) absorbs it
+        plan[0].out_hi = t.out_hi;
+        continue;
+      }
+      t.in_lo = t.out_lo - (uint32_t)back;
+    }
+    plan.push_back(t);
+  }
+  bool ok = true;
+  const size_t nt = plan.size();
+  const int nlanes = ctx().num_lanes;
+  for (size_t i = 0; i < nt && ok; i++) {
+    Tile& t = plan[i];
+    // the last tile stays on the caller's device: its state becomes the caller's
+    if (i > 0) t.device = (devices && device_count && i != nt - 1) ? devices[i % device_count] : h->device;
+    if (cudaSetDevice(t.device) != cudaSuccess) { ok = false; break; }
+    // tiles of one device go round its lanes (i / device_count: consecutive tiles sit on
+    // different devices)
+    const size_t per_dev = (devices && device_count) ? i / device_count : i;
+    t.lane = get_lane((int)(per_dev % (size_t)nlanes), g);
+    if (!t.lane) { ok = false; break; }
+    if (i == 0) {
+      t.h = h;
+    } else {
+      t.h = clone_for_tile(h, t.device, t.lane->stream);
+      if (!t.h) { ok = false; break; }
+    }
+    ok = enqueue_call(t.h, *t.lane, t.out_hi - t.in_lo, in + t.in_lo, out + t.in_lo, false,
+                      t.out_lo - t.in_lo);
+  }
+  for (auto& dl : ctx().lanes) {
+    if (cudaSetDevice(dl.first) != cudaSuccess) continue;
+    for (Lane& L : dl.second)
+      if (L.stream) cudaStreamSynchronize(L.stream);
+  }
+  cudaSetDevice(h->device);
+  if (ok) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("process_tiled", e, __FILE__, __LINE__);
+      ok = false;
+    }
+  }
+  after_sync(h);
+  if (ok && nt > 1) std::swap(*h, *plan[nt - 1].h);       // same device, same geometry: the stream goes on from here
+  for (size_t i = 1; i < nt; i++)
+    if (plan[i].h) release_tile_handle(plan[i].h);
+  if (reg_in) cudaHostUnregister(const_cast<float*>(in));
+  if (reg_out) cudaHostUnregister(out);
+  return ok;
+}
+
 bool stats_collect(Context& c) {
   for (auto& dl : c.lanes)
     for (Lane& L : dl.second)
       if (L.stream) SB_CUDA(cudaStreamSynchronize(L.stream));
   SB_CUDA(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lock(g_kev_mu);
+  // measurement knob: SB_TIMELINE=<file> appends "class,stream,start_ms,end_ms" of every timed
+  // launch relative to the first one (event times of different streams share one clock): a
+  // poor man's timeline of how the lanes interleave on the device
+  if (const char* path = getenv("SB_TIMELINE")) {
+    if (!g_kevents.empty()) {
+      if (FILE* f = fopen(path, "a")) {
+        for (KEvent& k : g_kevents) {
+          float a = 0.f, b = 0.f;
+          if (cudaEventElapsedTime(&a, g_kevents[0].e0, k.e0) == cudaSuccess &&
+              cudaEventElapsedTime(&b, g_kevents[0].e0, k.e1) == cudaSuccess)
+            fprintf(f, "%s,%p,%.4f,%.4f\n", kclass_name(k.cls), (void*)k.st, a, b);
+        }
+        fprintf(f, "#\n");
+        fclose(f);
+      }
+    }
+    cudaGetLastError();
+  }
   for (KEvent& k : g_kevents) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, k.e0, k.e1) == cudaSuccess) {

@@ -45,6 +45,8 @@ Lane* get_lane(int idx, const GeoK& g);
 bool process_call(Handle* h, uint32_t n, const float* in, float* out, bool device_io);
 bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* const* in,
                    float* const* out, bool device_io);
+bool process_tiled(Handle* h, uint32_t n, const float* in, float* out, uint32_t tiles,
+                   uint32_t warmup_frames, const int* devices, uint32_t device_count, uint32_t flags);
 bool stats_collect(Context& c);
 
 // sb_geometry.cu: private geometry for the FFT-only debug entry point

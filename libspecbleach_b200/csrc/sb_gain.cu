@@ -283,11 +283,13 @@ whitening_kernel(const GeoK g, const float* __restrict__ noise, int noise_stride
 struct PreArgs {
   int first_active, two_d, mask_stride;
   float alpha_max_user, tonal_gain;
+  int suppression;      // SuppressionType of the reference (suppression_engine.h:39-46), 0 = Berouti per bin
 };
 
-// one bin; *mg and *cl are only meaningful in 2D
+// one bin; *mg and *cl are only meaningful in 2D.  al_band: the alpha of the bin's band / frame
+// for the strategies that do not work per bin (N4: suppression_engine.c:135-241).
 __device__ __forceinline__ float pre_one(const PreArgs& a, float refv, float n, float m, float* mg,
-                                         float* cl) {
+                                         float* cl, float al_band) {
   float spec;
   if (a.two_d) {
     const float den = n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin;
@@ -297,14 +299,20 @@ __device__ __forceinline__ float pre_one(const PreArgs& a, float refv, float n, 
   } else {
     spec = refv;                     // 1D: alpha from the UNsmoothed power (spectral_denoiser.c:298-300)
   }
-  // suppression_engine.c:108-133
-  const float snr_db = 10.0f * log10f(spec / (n + kSpectralEps));
   float al;
-  if (snr_db <= kSnrLowDb) al = a.alpha_max_user;
-  else if (snr_db >= kSnrHighDb) al = kAlphaMin;
-  else {
-    const float ns = (snr_db - kSnrLowDb) / (kSnrHighDb - kSnrLowDb);
-    al = a.alpha_max_user - (ns * (a.alpha_max_user - kAlphaMin));
+  if (a.suppression == 0) {
+    // suppression_engine.c:108-133
+    const float snr_db = 10.0f * log10f(spec / (n + kSpectralEps));
+    if (snr_db <= kSnrLowDb) al = a.alpha_max_user;
+    else if (snr_db >= kSnrHighDb) al = kAlphaMin;
+    else {
+      const float ns = (snr_db - kSnrLowDb) / (kSnrHighDb - kSnrLowDb);
+      al = a.alpha_max_user - (ns * (a.alpha_max_user - kAlphaMin));
+    }
+  } else if (a.suppression == 4) {
+    al = kAlphaMin;        // SUPPRESSION_NONE (suppression_engine.c:269-274)
+  } else {
+    al = al_band;          // global SNR / critical-band SNR / masking thresholds: computed upstream
   }
   // tonal_reducer.c:92-113
   if (!(a.tonal_gain >= 0.999f)) {
@@ -321,10 +329,14 @@ __device__ __forceinline__ float pre_one(const PreArgs& a, float refv, float n, 
 __global__ void __launch_bounds__(512)
 gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
                 const float* __restrict__ noise_t, const float* __restrict__ mask,
-                float* __restrict__ Mg, float* __restrict__ alpha, float* __restrict__ clean) {
+                float* __restrict__ Mg, float* __restrict__ alpha, float* __restrict__ clean,
+                const float* __restrict__ sup_alpha) {
   const int i = a.first_active + blockIdx.x;
   const size_t ro = (size_t)i * g.Kp;
   const bool tonal = !(a.tonal_gain >= 0.999f);
+  // strategies 1 / 2: one alpha per band (sup_band_kernel); 3: one per bin (sup_alpha_kernel)
+  const bool per_band = a.suppression == 1 || a.suppression == 2;
+  const bool per_bin = a.suppression == 3;
   const float* __restrict__ mrow = mask + (size_t)i * a.mask_stride;
   for (int k = 4 * threadIdx.x; k < g.Kp; k += 4 * blockDim.x) {
     const float4 r4 = ld4(ref + ro + k), n4 = ld4(noise_t + ro + k);
@@ -335,7 +347,10 @@ gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
       if (k + u < g.K) {
         const float m = tonal ? mrow[k + u] : 0.f;
         mg[u] = 0.f; cl[u] = 0.f;
-        al[u] = pre_one(a, rv[u], nv[u], m, &mg[u], &cl[u]);
+        float alb = 1.f;
+        if (per_band) alb = sup_alpha[(size_t)i * kBandPitch + __ldg(&g.band_of_bin[k + u])];
+        else if (per_bin) alb = sup_alpha[ro + k + u];
+        al[u] = pre_one(a, rv[u], nv[u], m, &mg[u], &cl[u], alb);
       } else {
         al[u] = 1.f; mg[u] = 0.f; cl[u] = 0.f;
       }
@@ -348,15 +363,188 @@ gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
   }
 }
 
-// ---------------------------------------------------------------------------
-// (frame, band): band energies, spreading, tonality -> a_t[b]
-// ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
+// ---------------------------------------------------------------------------
+// N4: the oversubtraction strategies the shipped reference build never selects.
+// ---------------------------------------------------------------------------
+struct SupArgs {
+  int first_active, two_d, mode;   // mode 1: global SNR, 2: critical-band SNR
+  float strength;
+};
+
+__device__ __forceinline__ float sup_alpha_from_snr(float spec_sum, float noise_sum, float strength) {
+  // suppression_engine.c:147-162 / :177-194
+  const float snr_db = 10.0f * log10f(spec_sum / (noise_sum + kSpectralEps));
+  if (snr_db <= 0.0f) return strength;
+  if (snr_db >= 20.0f) return kAlphaMin;
+  const float ns = snr_db / 20.0f;
+  return ((1.0f - ns) * strength) + (ns * kAlphaMin);
+}
+
+// (frame, band): band sums of the reference spectrum and of the noise -> alpha per band
+// (calculate_critical_bands_snr), or their totals -> one alpha for the frame
+// (calculate_global_snr), written to all bands.  ref = smoothed SNR (2D) or power (1D).
+__global__ void __launch_bounds__(256)
+sup_band_kernel(const GeoK g, SupArgs a, const float* __restrict__ ref,
+                const float* __restrict__ noise_t, float* __restrict__ band_alpha) {
+  __shared__ float PS[kMaxBandTasks], PN[kMaxBandTasks];
+  __shared__ float BS[kBandPitch], BN[kBandPitch];
+  const int i = a.first_active + blockIdx.x;
+  const size_t ro = (size_t)i * g.Kp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int task = warp; task < g.ntask; task += nw) {
+    const int b = g.task_band[task];
+    const int k0 = g.task_k[task];
+    const int kend = g.task_band[task + 1 < g.ntask ? task + 1 : task] == b && task + 1 < g.ntask
+                         ? g.task_k[task + 1] : g.band_start[b + 1];
+    float ss = 0.f, sn = 0.f;
+    for (int k = k0 + lane; k < kend; k += 32) {
+      const float n = noise_t[ro + k];
+      float sp = ref[ro + k];
+      if (a.two_d) sp *= (n > kNlmNoiseFloorMin ? n : kNlmNoiseFloorMin);   // nlm_filter.c:481-508
+      ss += sp;
+      sn += n;
+    }
+    ss = warp_sum(ss);
+    sn = warp_sum(sn);
+    if (lane == 0) { PS[task] = ss; PN[task] = sn; }
+  }
+  __syncthreads();
+  if (threadIdx.x < kBandPitch) {
+    const int b = threadIdx.x;
+    float ss = 0.f, sn = 0.f;
+    if (b < g.nb)
+      for (int t = g.band_task0[b]; t < g.band_task0[b + 1]; t++) { ss += PS[t]; sn += PN[t]; }
+    BS[b] = ss;
+    BN[b] = sn;
+  }
+  __syncthreads();
+  if (threadIdx.x < kBandPitch) {
+    const int b = threadIdx.x;
+    float al = kAlphaMin;
+    if (a.mode == 1) {
+      float ss = 0.f, sn = 0.f;
+      for (int q = 0; q < g.nb; q++) { ss += BS[q]; sn += BN[q]; }
+      al = sup_alpha_from_snr(ss, sn, a.strength);
+    } else if (b < g.nb) {
+      al = sup_alpha_from_snr(BS[b], BN[b], a.strength);
+    }
+    band_alpha[(size_t)i * kBandPitch + b] = al;
+  }
+}
+
+// clean-signal estimate of calculate_masking_thresholds (suppression_engine.c:202-206): 1D only
+// (in 2D gain_pre_kernel has already written max(Mg - n, 0))
+__global__ void __launch_bounds__(512)
+sup_clean_kernel(const GeoK g, int first_active, const float* __restrict__ P,
+                 const float* __restrict__ noise_t, float* __restrict__ clean) {
+  const size_t ro = (size_t)(first_active + blockIdx.x) * g.Kp;
+  for (int k = 4 * threadIdx.x; k < g.Kp; k += 4 * blockDim.x) {
+    const float4 p = ld4(P + ro + k), n = ld4(noise_t + ro + k);
+    st4(clean + ro + k, make_float4(fmaxf(p.x - n.x, 0.f), fmaxf(p.y - n.y, 0.f), fmaxf(p.z - n.z, 0.f),
+                                    fmaxf(p.w - n.w, 0.f)));
+  }
+}
+
+// (frame, bin): masking threshold of the bin's band, floored by the absolute threshold of
+// hearing, -> noise-to-mask ratio -> alpha (suppression_engine.c:208-231; beta is 0 in both
+// processors: undersubtraction = 0)
+__global__ void __launch_bounds__(512)
+sup_alpha_kernel(const GeoK g, int first_active, float strength, const float* __restrict__ band_T,
+                 const float* __restrict__ noise_t, float* __restrict__ alpha_bin) {
+  __shared__ float SPLs[kBandPitch], VT[kBandPitch];
+  const int i = first_active + blockIdx.x;
+  const size_t ro = (size_t)i * g.Kp;
+  if (threadIdx.x < g.nb) {
+    const int b = threadIdx.x;
+    const float T = powf(band_T[(size_t)i * kBandPitch + b], kInvPower);   // band_T holds u = T^0.6
+    const float spl = (10.0f * log10f(T + kSpectralEps)) + g.spl_ref;      // absolute_hearing_thresholds.c:141-159
+    float vT = powf(10.0f, (spl - g.spl_ref) / 10.0f) - kSpectralEps;
+    if (vT < 0.0f) vT = 0.0f;
+    SPLs[b] = spl;
+    VT[b] = vT;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
+    float al = kAlphaMin;
+    if (k < g.K) {
+      const int b = __ldg(&g.band_of_bin[k]);
+      const float thr = (SPLs[b] >= __ldg(&g.abs_thr_spl[k])) ? VT[b] : __ldg(&g.abs_thr_lin[k]);
+      const float nmr_db = 10.0f * log10f(noise_t[ro + k] / (thr + kSpectralEps));
+      if (nmr_db <= 0.0f) al = kAlphaMin + ((strength - kAlphaMin) * 0.1f);
+      else if (nmr_db >= 20.0f) al = strength;
+      else {
+        const float nn = nmr_db / 20.0f;
+        al = ((1.0f - nn) * kAlphaMin) + (nn * strength);
+      }
+    }
+    alpha_bin[ro + k] = al;
+  }
+}
+
+// TRANSIENT_AWARE smoothing of the 1D processor (spectral_smoother.c:141-181): band energies of
+// the unsmoothed power -> transient_detector_process per band (transient_detector.c:66-111),
+// a recursion over frames with state (smoothed energies + initialised flag) -> onset weights.
+__global__ void __launch_bounds__(256)
+band_energy_kernel(const GeoK g, int first_active, const float* __restrict__ P, float* __restrict__ band_e) {
+  __shared__ float PS[kMaxBandTasks];
+  const int i = first_active + blockIdx.x;
+  const size_t ro = (size_t)i * g.Kp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int task = warp; task < g.ntask; task += nw) {
+    const int b = g.task_band[task];
+    const int k0 = g.task_k[task];
+    const int kend = g.task_band[task + 1 < g.ntask ? task + 1 : task] == b && task + 1 < g.ntask
+                         ? g.task_k[task + 1] : g.band_start[b + 1];
+    float ss = 0.f;
+    for (int k = k0 + lane; k < kend; k += 32) ss += P[ro + k];
+    ss = warp_sum(ss);
+    if (lane == 0) PS[task] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x < kBandPitch) {
+    const int b = threadIdx.x;
+    float ss = 0.f;
+    if (b < g.nb)
+      for (int t = g.band_task0[b]; t < g.band_task0[b + 1]; t++) ss += PS[t];
+    band_e[(size_t)i * kBandPitch + b] = ss;
+  }
+}
+
+constexpr float kTransientAlpha = 0.8f;          // configurations.h:152
+constexpr float kOnsetSensitivity = 0.25f;       // :151
+constexpr float kMinInnovationEnergy = 1e-10f;   // :150
+
+// one warp, lane = band: weights[f][b] in place of the energies; state[0..31] smoothed energies,
+// state[32] = 1 once initialised
+__global__ void onset_scan_kernel(int nb, int rows, float* __restrict__ band_e, float* __restrict__ state) {
+  const int b = threadIdx.x;
+  if (b >= kBandPitch) return;
+  float sm = state[b];
+  bool init = state[kBandPitch] != 0.f;
+  for (int f = 0; f < rows; f++) {
+    const float cur = band_e[(size_t)f * kBandPitch + b];
+    if (!init) { sm = cur; init = true; }
+    const float ratio = cur / (sm + 1e-9f);
+    float w = (ratio - 1.0f) / kOnsetSensitivity;
+    w = (cur < kMinInnovationEnergy) ? 0.0f : w;
+    w = fminf(fmaxf(w, 0.0f), 1.0f);
+    const float aa = (w > 0.0f) ? (kTransientAlpha * 0.5f) : kTransientAlpha;
+    sm = (cur * (1.0f - aa)) + (sm * aa);
+    band_e[(size_t)f * kBandPitch + b] = (b < nb) ? w : 0.f;
+  }
+  state[b] = sm;
+  if (b == 0 && rows > 0) state[kBandPitch] = 1.f;
+}
+
+// ---------------------------------------------------------------------------
+// (frame, band): band energies, spreading, tonality -> a_t[b]
+// ---------------------------------------------------------------------------
 __device__ __forceinline__ float spreading_gain(float dz, float level_db) {
   // masking_estimator.c:305-318
   const float s_up = fminf(fmaxf(15.0f - ((level_db - 40.0f) * 0.2f), 5.0f), 15.0f);
@@ -700,7 +888,8 @@ constexpr int kRs1Tile = 32, kRs1Ring = 5, kRs1Ahead = 3;
 
 __global__ void __launch_bounds__(256)
 rowscan1d_kernel(int ncols, int pitch, int rows, float smoothing, const float* P,
-                 const float* noise, float* Mg, float* stable, float* st_state, float* sp_state) {
+                 const float* noise, float* Mg, float* stable, float* st_state, float* sp_state,
+                 const float* __restrict__ onset, const int* __restrict__ band_of_bin) {
   __shared__ __align__(16) float ringP[kRs1Ring][kRs1Tile][32];
   __shared__ __align__(16) float ringN[kRs1Ring][kRs1Tile][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -735,9 +924,13 @@ rowscan1d_kernel(int ncols, int pitch, int rows, float smoothing, const float* P
     }
   };
   float st = 0.f, sp = 0.f;
+  // TRANSIENT_AWARE (spectral_smoother.c:141-181): the smoothing of a bin is scaled by
+  // 1 - onset weight of its band in that frame; onset == nullptr is the FIXED smoother
+  const float* ow = nullptr;
   if (warp == 0 && cv) {
     st = st_state[col];
     sp = sp_state[col];
+    if (onset) ow = onset + __ldg(&band_of_bin[col]);
   }
   for (int t = 0; t < kRs1Ahead; t++) load_tile(t);
   for (int t = 0; t < ntiles; t++) {
@@ -750,8 +943,10 @@ rowscan1d_kernel(int ncols, int pitch, int rows, float smoothing, const float* P
 #pragma unroll 8
       for (int r = 0; r < nr; r++) {
         const float c = pp[r * 32], n = pn[r * 32];
+        float sm = smoothing;
+        if (ow) sm = smoothing * (1.0f - ow[(size_t)(t * kRs1Tile + r) * kBandPitch]);
         float v = c;
-        if (c > sp) v = (smoothing * sp) + ((1.0f - smoothing) * c);
+        if (c > sp) v = (sm * sp) + ((1.0f - sm) * c);
         sp = v;
         const float cl = fmaxf(v - n, 0.0f);
         st = (kVetoSmoothing * cl) + ((1.0f - kVetoSmoothing) * st);
@@ -777,6 +972,7 @@ rowscan1d_kernel(int ncols, int pitch, int rows, float smoothing, const float* P
 struct FinalArgs {
   int first_active, frames, mask_stride, wt_stride, use_veto, residual;
   float depth, reduction, tonal, whitening;
+  int gain_type;        // GainCalculationType of the reference (gain_calculator.h:27-31), 0 = Wiener
 };
 
 __device__ __forceinline__ float final_gain(const GeoK& g, const FinalArgs& a, const float* prot, int k,
@@ -795,11 +991,30 @@ __device__ __forceinline__ float final_gain(const GeoK& g, const FinalArgs& a, c
     const float veto = bp * sc * a.depth;
     al = al + ((1.0f - al) * veto);
   }
-  // gain_calculator.c:27-69
-  const float sn = n * al;
   float gain;
-  if (sn > FLT_MIN) gain = (spec > sn) ? (spec - sn) / spec : 0.0f;
-  else gain = 1.0f;
+  if (a.gain_type == 2) {
+    // generalized_spectral_subtraction (gain_calculator.c:113-139) with beta = 0: both
+    // processors pass undersubtraction 0 (spectral_denoiser.c:296, spectral_2d_denoiser.c:399)
+    if (spec > FLT_MIN) {
+      const float ratio = n / spec;
+      const float ratio_sq = ratio * ratio;
+      if (ratio_sq < (1.0f / (al + 0.0f))) gain = fmaxf(sqrtf(fmaxf(1.0f - (al * ratio_sq), 0.0f)), 0.0f);
+      else gain = 0.0f;
+    } else {
+      gain = 1.0f;
+    }
+  } else {
+    const float sn = n * al;
+    if (a.gain_type == 1) {
+      // spectral_gating (gain_calculator.c:71-111)
+      if (sn > FLT_MIN) gain = (sn > spec) ? 0.0f : 1.0f;
+      else gain = 1.0f;
+    } else {
+      // wiener_subtraction (gain_calculator.c:27-69)
+      if (sn > FLT_MIN) gain = (spec > sn) ? (spec - sn) / spec : 0.0f;
+      else gain = 1.0f;
+    }
+  }
   // noise_floor_manager.c:94-157
   if (a.reduction >= 0.999f && a.tonal >= 0.999f) {
     gain = 1.0f;
@@ -978,10 +1193,53 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
     pa.mask_stride = a.mask_stride;
     pa.alpha_max_user = kAlphaMin + (a.strength * (kAlphaMax - kAlphaMin));
     pa.tonal_gain = a.tonal;
+    pa.suppression = a.suppression_type;
+    const float* refspec = a.two_d ? L.Shat : L.P;
+    const float* sup_alpha = nullptr;
+    if (a.suppression_type == 1 || a.suppression_type == 2) {
+      // N4: global / critical-band SNR -> one alpha per band row (L.band_a is free until the veto)
+      KTimer kt_(kcGainPre, st);
+      SupArgs sa;
+      sa.first_active = fa;
+      sa.two_d = a.two_d ? 1 : 0;
+      sa.mode = a.suppression_type;
+      sa.strength = a.strength;
+      sup_band_kernel<<<active, 256, 0, st>>>(g, sa, refspec, L.noise, L.band_a);
+      SB_LAUNCH_CHECK();
+      sup_alpha = L.band_a;
+    } else if (a.suppression_type == 3) {
+      // N4: masking thresholds of the clean-signal estimate max(spectrum - noise, 0) through the
+      // suppression engine's own masking estimator (same Bark tables; its own forward-masking
+      // state, h.d_band_state row 2) -> per-bin alpha in L.wt-free scratch: L.Yre (written last)
+      KTimer kt_(kcGainPre, st);
+      float* cleanp = L.stable;                       // 2D: filled by the plain pre pass below
+      if (a.two_d) {
+        PreArgs p0 = pa;
+        p0.suppression = 4;                           // alpha is recomputed afterwards
+        gain_pre_kernel<<<active, row_threads(g), 0, st>>>(g, p0, refspec, L.noise, a.mask, L.Mg, L.alpha,
+                                                           L.stable, nullptr);
+        SB_LAUNCH_CHECK();
+      } else {
+        cleanp = L.Mg;                                // 1D: Mg is only written by the smoother later
+        sup_clean_kernel<<<active, row_threads(g), 0, st>>>(g, fa, L.P, L.noise, L.Mg);
+        SB_LAUNCH_CHECK();
+      }
+      band_kernel<<<active, 256, 0, st>>>(g, fa, 0, cleanp, L.Xre, L.noise, L.band_a);
+      SB_LAUNCH_CHECK();
+      RsCoef fc;
+      for (int b = 0; b < 32; b++) fc.c[b] = b < g.nb ? g.fwd_pow[b] : 0.f;
+      rowscan_kernel<1><<<1, 256, 0, st>>>(g.nb, kBandPitch, active, L.band_a + (size_t)fa * kBandPitch,
+                                           L.band_T + (size_t)fa * kBandPitch, fc,
+                                           h.d_band_state + 2 * kBandPitch);
+      SB_LAUNCH_CHECK();
+      sup_alpha_kernel<<<active, 512, 0, st>>>(g, fa, a.strength, L.band_T, L.noise, L.Yre);
+      SB_LAUNCH_CHECK();
+      sup_alpha = L.Yre;
+    }
     {
       KTimer kt_(kcGainPre, st);
-    gain_pre_kernel<<<active, row_threads(g), 0, st>>>(g, pa, a.two_d ? L.Shat : L.P, L.noise, a.mask, L.Mg,
-                                          L.alpha, L.stable);
+    gain_pre_kernel<<<active, row_threads(g), 0, st>>>(g, pa, refspec, L.noise, a.mask, L.Mg,
+                                          L.alpha, L.stable, sup_alpha);
     SB_LAUNCH_CHECK();
     }
     if (use_veto || !a.two_d) {
@@ -993,9 +1251,19 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
                                                            h.d_stable);
       } else {
         const size_t o = (size_t)fa * g.Kp;
+        const float* onset = nullptr;
+        if (a.smoothing_type == 2) {
+          // N4: TRANSIENT_AWARE -- band energies of the unsmoothed power, onset weights per band
+          band_energy_kernel<<<active, 256, 0, st>>>(g, fa, L.P, L.band_T);
+          SB_LAUNCH_CHECK();
+          onset_scan_kernel<<<1, kBandPitch, 0, st>>>(g.nb, active, L.band_T + (size_t)fa * kBandPitch,
+                                                      h.d_band_state + 3 * kBandPitch);
+          SB_LAUNCH_CHECK();
+          onset = L.band_T + (size_t)fa * kBandPitch;
+        }
         rowscan1d_kernel<<<(g.K + 31) / 32, 256, 0, st>>>(g.K, g.Kp, active, a.smoothing, L.P + o,
                                                           L.noise + o, L.Mg + o, L.stable + o,
-                                                          h.d_stable, h.d_sp_prev);
+                                                          h.d_stable, h.d_sp_prev, onset, g.band_of_bin);
       }
       SB_LAUNCH_CHECK();
       }
@@ -1042,6 +1310,7 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
   fa2.reduction = a.reduction;
   fa2.tonal = a.tonal;
   fa2.whitening = a.whitening;
+  fa2.gain_type = a.gain_type;
   {
     KTimer kt_(kcFinal, st);
   final_kernel<<<M, row_threads(g), 0, st>>>(g, fa2, L.Xre, L.Xim, L.noise, L.Mg, L.alpha, L.stable,

@@ -120,6 +120,8 @@ struct StateHeader {
   uint64_t est_floats;
 };
 
+constexpr uint32_t kStateVersion = 2;   // 2: strategy selectors, five band-state rows
+
 struct StateScalars {
   Params prm;
   uint32_t params_loaded, block_count[4], available[4], profile_learned;
@@ -129,6 +131,7 @@ struct StateScalars {
   float nlm_h;
   int32_t last_adaptive_state;
   float aggressiveness_state;
+  int32_t gain_type, suppression_type, smoothing_type;
 };
 
 struct DevArray {
@@ -143,7 +146,7 @@ static std::vector<DevArray> state_arrays(Handle* h) {
       {&h->d_prof, 4 * Kp}, {&h->d_med_ring, (size_t)kMedianFrames * Kp},
       {&h->d_hist, (size_t)g.frame + g.hop}, {&h->d_tail[0], (size_t)g.frame},
       {&h->d_tail[1], (size_t)g.frame}, {&h->d_stable, Kp}, {&h->d_sp_prev, Kp},
-      {&h->d_band_state, (size_t)2 * kBandPitch}, {&h->d_floor, Kp}};
+      {&h->d_band_state, (size_t)kBandStateRows * kBandPitch}, {&h->d_floor, Kp}};
   if (h->two_d) {
     a.push_back({&h->d_X_hist_re, 4 * Kp});
     a.push_back({&h->d_X_hist_im, 4 * Kp});
@@ -183,7 +186,7 @@ bool state_save(Handle* h, void* blob, size_t bytes) {
   StateHeader hd;
   memset(&hd, 0, sizeof(hd));
   memcpy(hd.magic, "SBST", 4);
-  hd.version = 1;
+  hd.version = kStateVersion;
   hd.sample_rate = h->geo->sample_rate;
   hd.frame_ms = h->geo->frame_ms;
   hd.two_d = h->two_d ? 1u : 0u;
@@ -211,6 +214,9 @@ bool state_save(Handle* h, void* blob, size_t bytes) {
   sc.nlm_h = h->nlm_h;
   sc.last_adaptive_state = h->last_adaptive_state;
   sc.aggressiveness_state = h->aggressiveness_state;
+  sc.gain_type = h->gain_type;
+  sc.suppression_type = h->suppression_type;
+  sc.smoothing_type = h->smoothing_type;
   memcpy(p, &sc, sizeof(sc));
   p += sizeof(sc);
   for (int m = 0; m < 4; m++) {
@@ -235,7 +241,7 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
     return false;
   }
   memcpy(&hd, p, sizeof(hd));
-  if (memcmp(hd.magic, "SBST", 4) != 0 || hd.version != 1) {
+  if (memcmp(hd.magic, "SBST", 4) != 0 || hd.version != kStateVersion) {
     set_error_msg("specbleach-b200: not a state blob (magic / version)");
     return false;
   }
@@ -285,7 +291,8 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
     return false;
   }
   if (sc.med_write < 0 || sc.med_write >= kMedianFrames || sc.tail_cur < 0 || sc.tail_cur > 1 ||
-      sc.carry >= (uint32_t)gk.hop) {
+      sc.carry >= (uint32_t)gk.hop || sc.gain_type < 0 || sc.gain_type > 2 || sc.suppression_type < 0 ||
+      sc.suppression_type > 4 || sc.smoothing_type < 1 || sc.smoothing_type > 2) {
     set_error_msg("specbleach-b200: state blob holds out-of-range ring positions");
     return false;
   }
@@ -318,6 +325,9 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
   h->nlm_h = sc.nlm_h;
   h->last_adaptive_state = sc.last_adaptive_state;
   h->aggressiveness_state = sc.aggressiveness_state;
+  h->gain_type = sc.gain_type;
+  h->suppression_type = sc.suppression_type;
+  h->smoothing_type = sc.smoothing_type;
   for (int m = 0; m < 4; m++) {
     memcpy(h->prof_host[m].data(), p, (size_t)h->profile_size * sizeof(float));
     p += (size_t)h->profile_size * sizeof(float);

@@ -17,8 +17,7 @@
 // (K % 8 != 0, e.g. the single bin 1600 of K = 1601) has its centre clamped to K-1 and every
 // patch element clamped individually, so its patches are not aligned to the 8-bin groups of
 // the main kernel: nlm_tail_kernel below evaluates it in direct form with the reference's
-// accumulation order.  It touches one column group of the output and only reads S, so it runs
-// on a side stream next to the main kernels of the same call.
+// accumulation order.
 // (The first two generations of the main kernel -- direct form, 2.87 ms per 1333 targets, and
 // row-SSD sharing with mbarrier producer / reducer warps, 1.57 ms per 4096 -- were removed in
 // round 2; they are in the history of this file.)
@@ -26,9 +25,6 @@
 // This translation unit is compiled with -ftz=true: the reference runs NLM
 // under FTZ|DAZ (nlm_filter_avx.c:88, simd_utils.h:67-94).
 #include "sb_common.h"
-
-#include <map>
-#include <mutex>
 
 namespace sb {
 namespace {
@@ -203,49 +199,24 @@ nlm_tail_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int f
   }
 }
 
-// side stream of a lane stream for the tail kernel (created on the lane's device)
-struct TailAux {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-std::mutex g_aux_mu;
-std::map<cudaStream_t, TailAux> g_aux;
-
 }  // namespace
 
 bool launch_nlm(const GeoK& g, const float* S, int first_target_row, int targets, float h,
                 float* Shat, cudaStream_t st) {
   if (targets <= 0) return true;
   const int nfull = g.K / 8;
-  TailAux aux;
-  const bool tail = g.K % 8 != 0;
-  if (tail) {
-    {
-      std::lock_guard<std::mutex> lock(g_aux_mu);
-      TailAux& ref = g_aux[st];
-      if (!ref.stream) {
-        SB_CUDA(cudaStreamCreateWithFlags(&ref.stream, cudaStreamNonBlocking));
-        SB_CUDA(cudaEventCreateWithFlags(&ref.fork, cudaEventDisableTiming));
-        SB_CUDA(cudaEventCreateWithFlags(&ref.join, cudaEventDisableTiming));
-      }
-      aux = ref;
-    }
-    // fork: the tail block only reads S and writes its own output columns
-    SB_CUDA(cudaEventRecord(aux.fork, st));
-    SB_CUDA(cudaStreamWaitEvent(aux.stream, aux.fork, 0));
-    {
-      KTimer kt2(kcNlmTail, aux.stream);
-      nlm_tail_kernel<<<(targets + TAILT - 1) / TAILT, TAILT * 32, 0, aux.stream>>>(
-          S, g.Kp, g.K, nfull, first_target_row, targets, h, Shat, g.Kp);
-      SB_LAUNCH_CHECK();
-    }
-    SB_CUDA(cudaEventRecord(aux.join, aux.stream));
+  if (g.K % 8 != 0) {
+    // the tail block only reads S and writes its own output columns; it goes first because the
+    // persistent main kernel occupies every SM until it ends (on a side stream it would wait)
+    KTimer kt2(kcNlmTail, st);
+    nlm_tail_kernel<<<(targets + TAILT - 1) / TAILT, TAILT * 32, 0, st>>>(
+        S, g.Kp, g.K, nfull, first_target_row, targets, h, Shat, g.Kp);
+    SB_LAUNCH_CHECK();
   }
   if (nfull > 0) {
     KTimer kt(kcNlm, st);
     if (!launch_nlm3(g, S, first_target_row, targets, h, Shat, st)) return false;
   }
-  if (tail) SB_CUDA(cudaStreamWaitEvent(st, aux.join, 0));
   return true;
 }
 

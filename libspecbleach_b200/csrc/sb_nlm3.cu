@@ -703,6 +703,240 @@ nlm3_paste2_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, in
   out[(size_t)tau * pitchO + bs + j] = res;
 }
 
+
+// =============================================================================================
+// Fused, persistent form (round 2): ONE launch per call.  A CTA per SM takes (target tile, block
+// tile) work items from a global queue -- highest block tiles first, they hold the most accepted
+// candidates -- so there is no chunking and no wave quantisation (the two-pass form ran 442 CTAs
+// = 2.99 waves per chunk of 2176 targets and paid a partial wave plus a kernel boundary per
+// chunk).  The paste is the tile's epilogue: the bit fields never leave shared memory, the pasted
+// values come from the staged tile (its edge-replicated halo is clamp_index), and the weights are
+// read back from a scratch region private to the CTA a few microseconds after they were written,
+// i.e. from L2.  The two-pass form read flags and weights back in a second kernel; by then they
+// had left L2 (ncu, round 1: 123 MB of DRAM reads per chunk at a 32 % L2 hit rate, 6.4 x the
+// algorithmic traffic of the whole NLM), which is what bounded the paste kernel.
+// Paste order per (target, block): lanes over candidates by rank, then a fixed tree over the 8
+// lanes (as nlm3_paste2_kernel): deterministic, independent of tiling and scheduling.
+// =============================================================================================
+template <bool PK, int MAXREG, bool PERSIST>
+__global__ void __maxnreg__(MAXREG)
+nlm4_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
+            int targets, int last_row, float h, float* __restrict__ Wg, unsigned* __restrict__ queue,
+            float* __restrict__ out, int pitchO) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* sp = smem_raw;
+  float* tile = reinterpret_cast<float*>(sp);            sp += SMEM3_TILE;
+  unsigned* flags = reinterpret_cast<unsigned*>(sp);     sp += SMEM3_FLAGS;
+  unsigned* gate = reinterpret_cast<unsigned*>(sp);      sp += SMEM3_GATE;
+  float* prm = reinterpret_cast<float*>(sp);
+  unsigned* next_unit = reinterpret_cast<unsigned*>(prm + 2 * NB3);
+  unsigned* cur_tile = next_unit + 1;
+
+  const int nbt = (nfull + NB3 - 1) / NB3;               // block tiles
+  const int ntt = (targets + TT3 - 1) / TT3;             // target tiles
+  const int ntiles = nbt * ntt;
+  const int lane = threadIdx.x & 31;
+  // PERSIST: a CTA per SM pulls tiles from the queue.  Otherwise a CTA per tile (the hardware
+  // scheduler hands SMs to the other lanes' kernels as the grid drains) and the weight region is
+  // the SM's: one CTA per SM at a time (124 KB of shared memory each), %smid fixed for its life.
+  unsigned region = blockIdx.x;
+  if (!PERSIST) asm("mov.u32 %0, %%smid;" : "=r"(region));
+  float* Wcta = Wg + (size_t)region * ((size_t)TT3 * NB3 * WPITCH3);
+
+  for (int iter = 0;; iter++) {
+    if (PERSIST) {
+      if (threadIdx.x == 0) *cur_tile = atomicAdd(queue, 1u);
+      __syncthreads();                                   // also: the previous tile's epilogue is done
+    }
+    const int tidx = PERSIST ? (int)*cur_tile : (iter == 0 ? (int)blockIdx.x : ntiles);
+    if (tidx >= ntiles) break;
+    const int bt = nbt - 1 - tidx / ntt;                 // highest block tiles first
+    const int tt = tidx - (tidx / ntt) * ntt;
+    const int blk0 = bt * NB3;
+    const int tau0 = tt * TT3;
+    const int nT = (targets - tau0 < TT3) ? targets - tau0 : TT3;
+    const int row_t0 = first_target_row + tau0;          // S row of target 0 of this tile
+    const int c_origin = blk0 * 8 - 8;
+
+    // ---- stage rows t0-16 .. t0+nT+3 (clamped to the rows that exist), edge-replicated bins ----
+    for (int e = threadIdx.x; e < ROWS3 * GRP3 * 8; e += NTH3) {
+      const int r = e / (GRP3 * 8);
+      const int c_rel = e - r * (GRP3 * 8);
+      int c = c_origin + c_rel;
+      c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
+      int gr = row_t0 - kNlmPast + r;
+      gr = gr > last_row ? last_row : gr;
+      tile[r * PITCH3 + tcol3(c_rel)] = S[(size_t)gr * pitchS + c];
+    }
+    for (int e = threadIdx.x; e < TT3 * NB3 * FW3; e += NTH3) flags[e] = 0u;
+    if (threadIdx.x == 0) *next_unit = 0u;
+    if (threadIdx.x < NB3) {                              // 1/h_b^2 and 4 h_b^2 per paste block
+      float inv, thr;
+      block_params3(8 * (blk0 + threadIdx.x) + 4, K, h, &inv, &thr);
+      prm[threadIdx.x] = inv;
+      prm[NB3 + threadIdx.x] = thr;
+    }
+    __syncthreads();
+    // block energy gate per (target, paste block): nlm_filter_avx.c:123-129
+    if (threadIdx.x < TT3) {
+      unsigned bits = 0u;
+      const float* tr = tile + (kNlmPast + threadIdx.x) * PITCH3;
+      for (int bl = 0; bl < NB3; bl++) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) ssum += tr[SLOT3 * (bl + 1) + q];
+        if (ssum >= 1e-6f) bits |= 1u << bl;
+      }
+      gate[threadIdx.x] = bits;
+    }
+    __syncthreads();
+
+    {
+      Lane3 L;
+      L.tile = tile;
+      L.bl = lane >> 1;
+      L.g = lane & 1;
+      const int b = blk0 + L.bl;
+      L.active = b < nfull;
+      L.live = 0ull;
+      if (L.active)
+        for (int t = 0; t < TT3; t++) L.live |= (unsigned long long)((gate[t] >> L.bl) & 1u) << t;
+      L.flags = flags + L.bl * FW3;
+      L.wstride = NB3 * WPITCH3;
+      L.wout = Wcta + (size_t)L.bl * WPITCH3;
+      L.col_tg = SLOT3 * (L.bl + 1);
+      L.col_seg = SLOT3 * (L.bl + L.g);
+      const int bc = 8 * b + 4;
+      L.inv = prm[L.bl];
+      L.thr = prm[NB3 + L.bl];
+      L.hi_df = K - 1 - bc;
+      L.lo_clamp = (b == 0) && (L.g == 0);
+      const bool edge = (blk0 == 0) || (blk0 + NB3 >= nfull);
+#pragma unroll 1
+      for (;;) {
+        int u = 0;
+        if (lane == 0) u = (int)atomicAdd(next_unit, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= NUNIT3) break;
+        const int dti = c_units3[u][0], half = c_units3[u][1];
+        const int mid = (nT + 1) >> 1;
+        const int ta = half == 2 ? mid : 0;
+        const int tb = half == 1 ? mid : nT;
+        if (ta >= tb) continue;
+        if (PK) {
+          if (dti < 4 || dti > 17) walk_wrap3p(L, dti, ta, tb, edge);
+          else walk_plain3p(L, dti, ta, tb, edge);
+        } else {
+          if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
+          else walk_plain3(L, dti, ta, tb, edge);
+        }
+      }
+    }
+    __syncthreads();            // every weight of the tile is written, every bit set
+
+    // ---- epilogue: paste the tile ----
+    const int nbv = (nfull - blk0 < NB3) ? nfull - blk0 : NB3;      // valid paste blocks of this tile
+    const int npairs = nT * nbv;
+    const int j = threadIdx.x & 7;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);             // the 8 lanes of a pair
+    for (int pl = threadIdx.x >> 3; pl < npairs; pl += NTH3 / 8) {
+      const int tau = pl / nbv;
+      const int bl = pl - tau * nbv;
+      const float* trow = tile + (kNlmPast + tau) * PITCH3;         // frame t
+      const int colb = 8 * (bl + 1);                                // tile-relative column of bin bs
+      const float tv = trow[tcol3(colb + j)];
+      float res = tv;
+      if ((gate[tau] >> bl) & 1u) {
+        const unsigned* fpair = flags + (tau * NB3 + bl) * FW3;
+        // most pairs accepted nothing but themselves (the threshold 4 h_b^2 is far below the
+        // SSD of two noise patches): lane j looks at words j and j + 8, one vote decides
+        unsigned mine = fpair[j] | (j < FW3 - 8 ? fpair[j + 8] : 0u);
+        mine |= __shfl_xor_sync(gmask, mine, 4);
+        mine |= __shfl_xor_sync(gmask, mine, 2);
+        mine |= __shfl_xor_sync(gmask, mine, 1);
+        const float w_self = schraudolph_exp3(-0.0f);
+        if (mine == 0u) {
+          // the self candidate alone: acc = w v, wsum = w (w_self > 1e-10)
+          res = fmaf(w_self, tv, 0.f) / w_self;
+        } else {
+        // lanes over candidates by rank (ascending (dt, df), the self candidate included): lane j
+        // takes ranks j, j + 8, ...; weight and the eight pasted values are requested together.
+        // (Tried: lane j walking its own bits {j, j+8, j+16, j+24} of the twelve words without any
+        // ranking -- twelve divergent loops per pair, 1.7 x slower for the whole kernel.)
+        unsigned fw[FW3];
+        const uint4* fp = reinterpret_cast<const uint4*>(fpair);
+        const uint4 f0 = fp[0], f1 = fp[1], f2 = fp[2];
+        fw[0] = f0.x; fw[1] = f0.y; fw[2] = f0.z; fw[3] = f0.w;
+        fw[4] = f1.x; fw[5] = f1.y; fw[6] = f1.z; fw[7] = f1.w;
+        fw[8] = f2.x; fw[9] = f2.y; fw[10] = f2.z; fw[11] = f2.w;
+        constexpr int kSelf = kNlmPast * 17 + kNlmRangeFreq;        // (dt 0, df 0): always accepted
+        fw[kSelf >> 5] |= 1u << (kSelf & 31);
+        int cum[FW3 + 1];
+        cum[0] = 0;
+#pragma unroll
+        for (int i = 0; i < FW3; i++) cum[i + 1] = cum[i] + __popc(fw[i]);
+        const int n = cum[FW3];
+        const float* wp = Wcta + (size_t)(tau * NB3 + bl) * WPITCH3;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = 0.f;
+        float ws = 0.f;
+        for (int r0 = 0; r0 < n; r0 += 8) {
+          const int rank = r0 + j;
+          if (rank < n) {
+            unsigned word = fw[0];
+            int base = 0, wi = 0;
+#pragma unroll
+            for (int i = 1; i < FW3; i++)
+              if (rank >= cum[i]) { word = fw[i]; base = cum[i]; wi = i; }
+            const int p = 32 * wi + nth_set_bit(word, rank - base);   // candidate index dti * 17 + dfi
+            const int dti = (p * 241) >> 12;                          // p / 17 for p < 357
+            const int c0 = colb + p - 17 * dti - kNlmRangeFreq;       // tile column of bin bs + df
+            float wgt = (p == kSelf) ? w_self : __ldcg(wp + p);       // written by this CTA: L2, not L1
+            const float* prow = trow + (dti - kNlmPast) * PITCH3;     // frame t + dt
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int c = c0 + i;                                   // halo column = clamp(bs + i + df)
+              v[i] = prow[c + 4 * (c >> 3)];                          // tcol3(c)
+            }
+            if (wgt < kNlmMinWeight) wgt = 0.f;                       // nlm_filter_avx.c:219-221
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = fmaf(wgt, v[i], acc[i]);
+            ws += wgt;
+          }
+        }
+        // transposing butterfly over the 8 lanes of the pair: lane j ends with bin j
+        float a4[4], a2[2], a1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float send = (j & 4) ? acc[i] : acc[i + 4];
+          const float keep = (j & 4) ? acc[i + 4] : acc[i];
+          a4[i] = keep + __shfl_xor_sync(gmask, send, 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const float send = (j & 2) ? a4[i] : a4[i + 2];
+          const float keep = (j & 2) ? a4[i + 2] : a4[i];
+          a2[i] = keep + __shfl_xor_sync(gmask, send, 2);
+        }
+        {
+          const float send = (j & 1) ? a2[0] : a2[1];
+          const float keep = (j & 1) ? a2[1] : a2[0];
+          a1 = keep + __shfl_xor_sync(gmask, send, 1);
+        }
+        ws += __shfl_xor_sync(gmask, ws, 4);
+        ws += __shfl_xor_sync(gmask, ws, 2);
+        ws += __shfl_xor_sync(gmask, ws, 1);
+        res = (ws > kNlmMinWeight) ? a1 / ws : tv;                  // nlm_filter_avx.c:237-243
+        }
+      }
+      out[(size_t)(tau0 + tau) * pitchO + 8 * (blk0 + bl) + j] = res;
+    }
+    // the loop head's barrier keeps the next tile's staging behind this epilogue
+  }
+}
+
 }  // namespace
 
 // Targets per chunk: close to CHUNK3, and such that the grid of the distance kernel (target tiles
@@ -730,6 +964,7 @@ struct Scratch3 {
   float* W = nullptr;
   unsigned* F = nullptr;
   size_t pairs = 0;
+  bool fused = false;    // sized for the fused kernel (per-CTA regions) rather than per chunk
 };
 static std::mutex g_scratch_mu;
 static std::map<cudaStream_t, Scratch3> g_scratch;
@@ -748,6 +983,72 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
                                (int)SMEM3));
   SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)SMEM3));
+  // measurement knob: SB_NLM_FUSED=0 selects the two-pass form (distance kernel + paste kernel
+  // per chunk of ~2k targets)
+  static const bool fused = [] {
+    const char* e = getenv("SB_NLM_FUSED");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (fused) {
+    // measurement knob: SB_NLM_MAXREG=168 lets the kernel use the whole register file of its SM
+    // (default 128: a quarter of the registers, 100 KB of shared memory and the idle issue slots
+    // of the SM stay available to the kernels of the other lanes)
+    static const int maxreg = [] {
+      const char* e = getenv("SB_NLM_MAXREG");
+      return e ? atoi(e) : 128;
+    }();
+    // measurement knob: SB_NLM_PERSIST=1: a CTA per SM and a tile queue instead of a CTA per tile
+    static const bool persist = [] {
+      const char* e = getenv("SB_NLM_PERSIST");
+      return e ? atoi(e) != 0 : false;
+    }();
+    const void* fn;
+    if (persist)
+      fn = packed ? (maxreg > 128 ? (const void*)nlm4_kernel<true, 168, true> : (const void*)nlm4_kernel<true, 128, true>)
+                  : (maxreg > 128 ? (const void*)nlm4_kernel<false, 168, true> : (const void*)nlm4_kernel<false, 128, true>);
+    else
+      fn = packed ? (maxreg > 128 ? (const void*)nlm4_kernel<true, 168, false> : (const void*)nlm4_kernel<true, 128, false>)
+                  : (maxreg > 128 ? (const void*)nlm4_kernel<false, 168, false> : (const void*)nlm4_kernel<false, 128, false>);
+    SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM3));
+    int dev = 0, sms = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = ((nfull + NB3 - 1) / NB3) * ((targets + TT3 - 1) / TT3);
+    const int ctas = persist ? (ntiles < sms ? ntiles : sms) : ntiles;
+    Scratch3 sc;
+    {
+      std::lock_guard<std::mutex> lock(g_scratch_mu);
+      Scratch3& ref = g_scratch[st];
+      // W: one private region of TT3 x NB3 pairs per CTA; F: the tile queue counter
+      const size_t need = (size_t)sms * TT3 * NB3;
+      if (ref.pairs < need || !ref.fused) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (ref.W) cudaFree(ref.W);
+        if (ref.F) cudaFree(ref.F);
+        ref = Scratch3();
+        SB_CUDA(cudaMalloc(&ref.W, need * WPITCH3 * sizeof(float)));
+        SB_CUDA(cudaMalloc(&ref.F, 256));
+        ref.pairs = need;
+        ref.fused = true;
+      }
+      sc = ref;
+    }
+    SB_CUDA(cudaMemsetAsync(sc.F, 0, sizeof(unsigned), st));
+    const int last_row = first_target_row + targets - 1 + kNlmFuture;
+    {
+      const float* S_ = S;
+      int pitchS = g.Kp, K_ = g.K, nfull_ = nfull, ftr = first_target_row, tg = targets, lr = last_row;
+      float h_ = h;
+      float* W_ = sc.W;
+      unsigned* Q_ = sc.F;
+      float* out_ = Shat;
+      int pitchO = g.Kp;
+      void* args[] = {&S_, &pitchS, &K_, &nfull_, &ftr, &tg, &lr, &h_, &W_, &Q_, &out_, &pitchO};
+      SB_CUDA(cudaLaunchKernel(fn, dim3(ctas), dim3(NTH3), args, SMEM3, st));
+    }
+    SB_LAUNCH_CHECK();
+    return true;
+  }
   const int chunk = nlm3_chunk_targets(g.K);
   // measurement knob: SB_NLM_PASTE=1 selects the first paste form (lanes over bins)
   static const int paste_form = [] {
@@ -760,7 +1061,7 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
     Scratch3& ref = g_scratch[st];
     // sized for the largest chunk seen on this stream (small sub-calls keep it small)
     const size_t need = (size_t)(targets < chunk ? targets : chunk) * (size_t)nfull;
-    if (ref.pairs < need) {
+    if (ref.pairs < need || ref.fused) {
       SB_CUDA(cudaStreamSynchronize(st));
       if (ref.W) cudaFree(ref.W);
       if (ref.F) cudaFree(ref.F);

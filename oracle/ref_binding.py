@@ -74,17 +74,30 @@ def available() -> bool:
 
 
 _lib = None
+_variants: dict = {}
+
+# build variants of the reference (oracle/Makefile, target `variants`): the
+# compile-time selectors of the processors pinned to the branches the shipped build never takes
+VARIANTS = ("gates", "gss", "sup_global", "sup_bands", "sup_masking", "sup_none", "transient")
 
 
-def load():
-    """dlopen the reference build and declare prototypes (idempotent)."""
+def variant_path(name: str) -> Path:
+    return _HERE / "_ref" / "variants" / f"libspecbleach_ref_{name}.so"
+
+
+def load(variant: str | None = None):
+    """dlopen the reference build (or one of its build variants) and declare prototypes
+    (idempotent per library)."""
     global _lib
-    if _lib is not None:
+    if variant is None and _lib is not None:
         return _lib
-    if not REF_SO.exists():
+    if variant is not None and variant in _variants:
+        return _variants[variant]
+    path = REF_SO if variant is None else variant_path(variant)
+    if not path.exists():
         raise FileNotFoundError(
-            f"{REF_SO} missing: run `make -C oracle` where /root/reference exists")
-    lib = C.CDLL(str(REF_SO))
+            f"{path} missing: run `make -C oracle` where /root/reference exists")
+    lib = C.CDLL(str(path))
     fp = C.POINTER(C.c_float)
     for pre in ("specbleach_", "specbleach_2d_"):
         g = lambda n: getattr(lib, pre + n)
@@ -122,7 +135,10 @@ def load():
     lib.nlm_filter_push_frame.argtypes = [C.c_void_p, fp]
     lib.nlm_filter_process.restype = C.c_bool
     lib.nlm_filter_process.argtypes = [C.c_void_p, fp]
-    _lib = lib
+    if variant is None:
+        _lib = lib
+    else:
+        _variants[variant] = lib
     return lib
 
 
@@ -133,8 +149,8 @@ def _fp(a: np.ndarray):
 class RefDenoiser:
     """Thin OO wrapper over the reference's handle API (1D or 2D)."""
 
-    def __init__(self, sample_rate: int, frame_ms: float, two_d: bool = True):
-        self.lib = load()
+    def __init__(self, sample_rate: int, frame_ms: float, two_d: bool = True, variant: str | None = None):
+        self.lib = load(variant)
         self.pre = "specbleach_2d_" if two_d else "specbleach_"
         self.h = self._f("initialize")(int(sample_rate), float(frame_ms))
         if not self.h:

@@ -276,3 +276,100 @@ def test_config1_speech_wav_demo_flow(gpu, ref, tmp_path):
     assert np.array_equal(y, got)                      # tool == API, bit for bit (chunking-invariant)
     print(f"config 1: max_abs={err:.3e} snr={snr:.1f} dB; reference {x.shape[0] / sr / t_ref:.1f}x realtime "
           f"(1 thread, 512-sample calls), CUDA path through 512-sample calls {x.shape[0] / sr / t_gpu:.1f}x")
+    import json
+    rec = root / "gpurun_out"
+    if rec.is_dir():
+        (rec / "config1_speech_wav.json").write_text(json.dumps({
+            "max_abs": err, "snr_db": snr, "audio_seconds": x.shape[0] / sr,
+            "reference_x_realtime_1_thread_512_sample_calls": x.shape[0] / sr / t_ref,
+            "cuda_x_realtime_512_sample_calls": x.shape[0] / sr / t_gpu}, indent=1))
+
+
+@pytest.mark.parametrize("two_d", [True, False], ids=["2d", "1d"])
+def test_c_abi_tiled_call_matches_reference_and_monolithic(gpu, ref, two_d):
+    """N3 as a product path: specbleach_b200_process_tiled (C ABI) on one 60 s stream, 6 tiles over
+    the engine's lanes.  (a) against the REFERENCE build, whole output, BASELINE tolerance;
+    (b) bit-identical to the monolithic specbleach[_2d]_process; (c) the handle continues the
+    stream afterwards exactly as the monolithic handle does (state of the last tile adopted);
+    (d) odd call sizes (carry != 0 at the call) and pageable buffers; (e) refusals."""
+    sr = 48000
+    prm = P2D if two_d else P1D
+    x = synth(64.0, sr, 88)
+    head, body, rest = x[:sr + 777], x[sr + 777:61 * sr + 123], x[61 * sr + 123:]   # odd cuts: carry != 0
+    r = ref.RefDenoiser(sr, 50.0, two_d)
+    r.load_parameters(learn_noise=1)
+    want = [r.process(head)]
+    r.load_parameters(**prm)
+    want += [r.process(body, 1 << 18), r.process(rest)]
+    want = np.concatenate(want)
+
+    def run(tiled):
+        d = gpu.Denoiser(sr, 50.0, two_d)
+        d.load_parameters(learn_noise=1)
+        ys = [d.process(head)]
+        d.load_parameters(**prm)
+        ys.append(d.process_tiled(body, tiles=6, warmup_frames=512) if tiled else d.process(body))
+        ys.append(d.process(rest, 5000))
+        return np.concatenate(ys)
+
+    mono, tiled = run(False), run(True)
+    err, snr = assert_parity(tiled, want, f"tiled C-ABI call vs reference, two_d={two_d}")
+    same = np.array_equal(tiled, mono)
+    print(f"tiled vs reference: {err:.3e} / {snr:.1f} dB; vs monolithic CUDA: "
+          f"{'bit-identical' if same else float(np.max(np.abs(tiled - mono)))}")
+    assert same
+    d = gpu.Denoiser(sr, 50.0, two_d)
+    d.load_parameters(learn_noise=1)
+    with pytest.raises(RuntimeError):
+        d.process_tiled(body, tiles=4)                                   # learn mode
+    d.load_parameters(**dict(prm, adaptive_noise=1, noise_estimation_method=0))
+    with pytest.raises(RuntimeError):
+        d.process_tiled(body, tiles=4)                                   # adaptive needs the flag
+    buf = body.copy()
+    d.load_parameters(**prm)
+    with pytest.raises(RuntimeError):
+        d.process_tiled(buf, tiles=4, out=buf)                           # in place
+
+
+def test_c_abi_tiled_call_adaptive_is_an_approximation(gpu, ref):
+    """adaptive SPP-MMSE / Martin through time tiles: allowed by flag, and the error against the
+    reference is MEASURED (printed and recorded), not assumed: the estimators' long memories make
+    the tiles approximate."""
+    from libspecbleach_b200.synth import nonstationary_noise
+    import json
+    from pathlib import Path
+    sr = 44100
+    x = nonstationary_noise(60.0, sr, 5)
+    res = {}
+    for method, name in ((0, "spp_mmse"), (2, "martin")):
+        prm = dict(P2D, adaptive_noise=1, noise_estimation_method=method)
+        want = run_flow(ref.RefDenoiser(sr, 50.0, True), x, 0, prm, 1 << 18)
+        d = gpu.Denoiser2D(sr, 50.0)
+        d.load_parameters(**prm)
+        got = d.process_tiled(x, tiles=4, warmup_frames=1024, allow_adaptive=True)
+        dd = got.astype(np.float64) - want
+        err = float(np.max(np.abs(dd)))
+        snr = 10 * np.log10(float(np.sum(want.astype(np.float64) ** 2)) / max(1e-300, float(np.sum(dd * dd))))
+        res[name] = {"max_abs": err, "snr_db": snr}
+        print(f"tiled adaptive {name}: max_abs={err:.3e} snr={snr:.1f} dB (4 tiles, 1024 warm-up frames)")
+        assert np.all(np.isfinite(got)) and snr > 20.0
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    if out.is_dir():
+        (out / "tiled_adaptive_error.json").write_text(json.dumps(res, indent=1))
+
+
+def test_c_abi_tiled_call_across_two_devices(gpu):
+    """tiles dealt to the lanes of two GPUs of one process: bit-identical to one GPU."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sr = 48000
+    x = synth(60.0, sr, 89)
+
+    def run(devices):
+        d = gpu.Denoiser2D(sr, 50.0)
+        d.load_parameters(learn_noise=1)
+        a = d.process(x[:sr])
+        d.load_parameters(**P2D)
+        return np.concatenate([a, d.process_tiled(x[sr:], tiles=8, warmup_frames=512, devices=devices)])
+
+    assert np.array_equal(run(None), run([0, 1]))

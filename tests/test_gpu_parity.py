@@ -9,9 +9,12 @@ import numpy as np
 import pytest
 
 from common import (GOLDEN_CASES, P1D, P2D, assert_parity, assert_parity_discontinuous, load_golden,
-                    run_flow)
+                    parity, run_flow)
 
 pytestmark = pytest.mark.gpu
+
+# bench.py's parameters for configs[1] (tonal_reduction 0, unlike P2D)
+P2D_BENCH = dict(P2D, tonal_reduction=0.0)
 
 
 def synth(seconds, sr, seed):
@@ -410,3 +413,101 @@ def test_first_paste_form_still_matches_golden():
     env = dict(os.environ, SB_NLM_PASTE="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _record(name, payload):
+    """measurements made as a side effect of a test, kept for BASELINE.md / DESIGN.md"""
+    import json
+    from pathlib import Path
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    if out.is_dir():
+        (out / f"{name}.json").write_text(json.dumps(payload, indent=1))
+
+
+def test_full_length_config2_matches_reference_build(gpu, ref):
+    """the full-size tests anchored only a prefix to the oracle.  Here ONE WHOLE channel
+    of the configs[1] bench input (600 s, 48 000 frames: learn 1 s + denoise 599 s, >= 4 internal
+    sub-calls, every NLM tile boundary) goes through the reference build (4 OpenMP threads, the
+    library default) and through the CUDA path, and every output sample is compared."""
+    import time
+    sr = 48000
+    x = synth(600.0, sr, 20260002)                     # channel 0 of bench.py's file on rank 0
+    ref.set_threads(4)
+    r = ref.RefDenoiser(sr, 50.0, True)
+    t0 = time.perf_counter()
+    want = run_flow(r, x, sr, P2D_BENCH, 1 << 20)
+    t_ref = time.perf_counter() - t0
+    ref.set_threads(1)
+    d = gpu.Denoiser2D(sr, 50.0)
+    t0 = time.perf_counter()
+    got = run_flow(d, x, sr, P2D_BENCH, None)
+    t_gpu = time.perf_counter() - t0
+    err, snr = assert_parity(got, want, "config 2, whole 600 s channel")
+    n_bad = int(np.sum(np.abs(got.astype(np.float64) - want) > 1e-5))
+    print(f"config 2 full length: max_abs={err:.3e} snr={snr:.1f} dB, samples off by > 1e-5: {n_bad}; "
+          f"reference {600.0 / t_ref:.1f}x realtime mono (4 OMP threads, {t_ref:.1f} s), "
+          f"CUDA path through specbleach_2d_process with pageable buffers {600.0 / t_gpu:.0f}x")
+    _record("full_length_config2", {"max_abs": err, "snr_db": snr, "samples_gt_1e-5": n_bad,
+                                    "ref_seconds_4_omp_threads": t_ref, "gpu_seconds_dropin_pageable": t_gpu,
+                                    "audio_seconds": 600.0})
+
+
+def test_long_adaptive_config4_matches_reference_build(gpu, ref, tmp_path):
+    """10 min of the configs[3] input (44.1 kHz, non-stationary noise) through the adaptive 2D path
+    with SPP-MMSE: 48 000 frames of a per-bin recursion that feeds back its own estimate, long
+    enough for a rounding-level difference to drift if it were going to.
+
+    (a) with a profile learned on the first second the tonal detector works on the static MAX
+        profile and the path is continuous: the WHOLE output must meet the BASELINE tolerance,
+        and the last minute must be as good as the first (no drift).
+    (b) without a learned profile (the bench flow) the tonal mask is re-detected on every frame's
+        noise estimate with a hard 1.41 peak ratio (tonal_detector.c:24-162), and the REFERENCE
+        ITSELF is not reproducible at the tolerance: a 1-ULP perturbation of its input moves it by
+        2.5e-4 / 85 dB over these 10 minutes (measured).  No implementation
+        with another FFT rounding can do better than that, so the CUDA path is held to the
+        reference's own self-consistency: not further from the reference than the perturbed
+        reference is (6 dB margin), and out of tolerance in at most two more minutes."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    from libspecbleach_b200.synth import nonstationary_noise
+    sr = 44100
+    n = 60 * sr
+    x = nonstationary_noise(600.0, sr, 20260004)
+    prm = dict(P2D, adaptive_noise=1, noise_estimation_method=0)
+    # three 10-minute reference runs side by side, each in its own process (tests/ref_long_run.py)
+    helper = str(Path(__file__).resolve().parent / "ref_long_run.py")
+    jobs = [(sr, 0, str(tmp_path / "learned.npy")), (0, 0, str(tmp_path / "exact.npy")),
+            (0, 1, str(tmp_path / "perturbed.npy"))]
+    procs = [subprocess.Popen([sys.executable, helper, str(a), str(b), c]) for a, b, c in jobs]
+    for p in procs:
+        assert p.wait(timeout=900) == 0
+    want_l, want, pert = (np.load(c) for _, _, c in jobs)
+    # (a) learned profile
+    got_l = run_flow(gpu.Denoiser2D(sr, 50.0), x, sr, prm, None)
+    err, snr = assert_parity(got_l, want_l, "config 4 input, learned profile, 10 min SPP-MMSE")
+    e0, s0 = assert_parity(got_l[:n], want_l[:n], "first minute")
+    e1, s1 = assert_parity(got_l[-n:], want_l[-n:], "last minute")
+    print(f"10 min SPP-MMSE, learned profile: max_abs={err:.3e} snr={snr:.1f} dB; first minute {s0:.1f} dB, "
+          f"last minute {s1:.1f} dB")
+    # (b) unlearned: against the reference's own reproducibility
+    got = run_flow(gpu.Denoiser2D(sr, 50.0), x, 0, prm, None)
+    assert np.all(np.isfinite(got))
+    e_c, s_c = parity(got, want)
+    e_r, s_r = parity(pert, want)
+    bad_c = bad_r = 0
+    for m in range(10):
+        ec, sc = parity(got[m * n:(m + 1) * n], want[m * n:(m + 1) * n])
+        er, sr_ = parity(pert[m * n:(m + 1) * n], want[m * n:(m + 1) * n])
+        bad_c += not (ec <= 1e-4 and sc >= 90.0)
+        bad_r += not (er <= 1e-4 and sr_ >= 90.0)
+    print(f"10 min SPP-MMSE, no learned profile: CUDA vs reference {e_c:.3e} / {s_c:.1f} dB "
+          f"({bad_c} of 10 minutes out of tolerance); reference vs 1-ULP-perturbed reference "
+          f"{e_r:.3e} / {s_r:.1f} dB ({bad_r} minutes)")
+    assert (e_c <= 1e-4 and s_c >= 90.0) or s_c >= s_r - 6.0
+    assert bad_c <= bad_r + 2
+    _record("long_adaptive_config4", {
+        "learned": {"max_abs": err, "snr_db": snr, "first_minute_snr_db": s0, "last_minute_snr_db": s1},
+        "unlearned_cuda_vs_reference": {"max_abs": e_c, "snr_db": s_c, "minutes_out_of_tolerance": int(bad_c)},
+        "unlearned_reference_vs_perturbed_reference": {"max_abs": e_r, "snr_db": s_r,
+                                                       "minutes_out_of_tolerance": int(bad_r)}})

@@ -138,3 +138,23 @@ def test_latency_quirk(ref):
     d1 = ref.RefDenoiser(48000, 50.0, False)
     assert d1.latency() == 2400 and d1.profile_size() == 1601
     assert math.isclose(float(snp.db_to_coeff(-20.0)), 0.1, rel_tol=1e-6)
+
+
+def test_reference_variant_builds_load_and_differ(ref):
+    """oracle/variants: rebuilds of the reference with one compile-time strategy selector pinned
+    (N4).  Every variant must load, run both denoisers and differ from the shipped build (the
+    transient-aware smoother only exists in the 1D processor)."""
+    import numpy as np
+    from libspecbleach_b200.synth import speech_plus_noise
+    from common import P1D, P2D, run_flow
+    if not all(ref.variant_path(v).exists() for v in ref.VARIANTS):
+        pytest.skip("oracle/_ref/variants not built (make -C oracle variants)")
+    sr = 48000
+    x = speech_plus_noise(2.5, sr, 3)
+    for two_d, prm in ((True, P2D), (False, dict(P1D, smoothing_factor=40.0))):
+        base = run_flow(ref.RefDenoiser(sr, 50.0, two_d), x, sr, prm, 4096)
+        for v in ref.VARIANTS:
+            y = run_flow(ref.RefDenoiser(sr, 50.0, two_d, variant=v), x, sr, prm, 4096)
+            assert np.all(np.isfinite(y))
+            changed = float(np.max(np.abs(y - base))) > 1e-4
+            assert changed == (not (v == "transient" and two_d)), (v, two_d)
