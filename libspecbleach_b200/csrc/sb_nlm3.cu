@@ -108,6 +108,7 @@ struct Lane3 {
   bool lo_clamp;          // paste block 0, lower half: df < -4 clamp to centre 0
   bool active;
   float thr, inv;
+  float neg1;             // -1 as a run-time value (SB_NLM_SUB_AS_FMA experiment)
 };
 
 // row terms of the 9 candidates of this lane for target-side row `ra` against row `rp`
@@ -125,7 +126,11 @@ __device__ __forceinline__ void rowterms3(const Lane3& L, int ra, int rp, float 
     float r = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
+#ifdef SB_NLM_SUB_AS_FMA
+      const float d = fmaf(seg[c + q], L.neg1, tg[q]);   // experiment: the subtraction on the FFMA path
+#else
       const float d = tg[q] - seg[c + q];
+#endif
       r = fmaf(d, d, r);
     }
     R[c] = r;
@@ -280,24 +285,34 @@ __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int ta, int 
 // Packed form of the row walk (sm_100a FFMA2 / FADD2: two FP32 operations per issue slot on an
 // aligned register pair; tools/microbench/fp32_pipes.cu: same FLOP rate as FFMA, half the issue
 // slots).  The distance kernel is issue-bound (75 % issue active, FMA pipe 52 %, 66 % of its
-// instructions FADD / FFMA), so halving the FP32 issue slots is what is left to gain.
-//  * row term of an even candidate c = 2m: the pairs (q, q+1), q = 0, 2, 4, 6 of target and
-//    partner are aligned register pairs of the LDS.128 results: 4 FADD2 + 4 FFMA2, then x + y;
-//  * odd candidate c = 2m + 1: the partner pairs (c+q, c+q+1) are aligned for ODD q, so the
-//    target is also kept shifted by one ((t1,t2) (t3,t4) (t5,t6): 6 register moves per row):
-//    3 FADD2 + 3 FFMA2, and the two end elements q = 0, 7 as scalar FADD + FFMA into x and y;
-//  * the delay tree and the wrapped walker's age update add candidate PAIRS (c, c+1).
-// Per plain row step 110 instead of 171 FP32-pipe issue slots.  The sums associate differently
-// from the scalar form ((q even) + (q odd)), deterministically.
+// instructions FADD / FFMA), so halving the FP32 issue slots of the row terms is what is left.
+//
+// The two halves of a register pair are two consecutive ROWS of the tile: the tile is staged
+// row-interleaved, bin c of rows (r, r + 1) side by side, so that an LDS.128 delivers two bins of a
+// row pair and every (target, partner) operand of the packed instructions is an aligned register
+// pair as it comes out of the load -- no shuffling of registers, for any candidate offset.  A lag
+// can be odd, hence two copies of the tile: E pairs rows (2m, 2m + 1), O pairs rows (2m - 1,
+// 2m); the target side always reads E (the walk advances two rows per iteration from an even
+// row), the partner side reads E or O by the parity of row + lag.  The row terms of both rows
+// come out of 8 FADD2 + 8 FFMA2 per candidate (16 + 16 scalar instructions before); the delay tree
+// and the wrapped walker's ages then take the two halves as two ordinary row steps.
+// Per plain row step 99 instead of 171 FP32-pipe issue slots, per wrapped one 288 instead of 432.
+// (A first packed form paired neighbouring BINS: the odd candidates needed a target shifted by
+// one register, and ptxas spent ~45 register moves per row step on pair alignment -- 1 % gain.)
 // ---------------------------------------------------------------------------------------------
-struct RowT {          // row terms / distances of the 9 candidates: pairs (0,1) (2,3) (4,5) (6,7), and 8
-  float2 p[4];
-  float s;
-};
+constexpr int SLOTP = 20;                   // floats per column group: 8 bins x 2 rows + 4 pad (80 B apart:
+                                            // a quarter-warp's LDS.128 hit 32 distinct banks)
+constexpr int PITCHP = GRP3 * SLOTP;        // 360 floats per row pair
+constexpr int NPAIR = ROWS3 / 2;            // E: 42 pairs, rows (2m, 2m + 1)
+constexpr int NPAIRO = NPAIR + 1;           // O: 43 pairs, rows (2m - 1, 2m): (-1 -> 0, 0) ... (83, 84 -> 83)
+constexpr size_t SMEMP_TILE = sizeof(float) * (size_t)(NPAIR + NPAIRO) * PITCHP;   // E and O copies
+constexpr size_t SMEMP = SMEMP_TILE + SMEM3_FLAGS + SMEM3_GATE + SMEM3_PRM;
 
-// a - b on a register pair.  sub.f32x2 is one FADD2 with the negate modifier on b; written as
-// __fadd2_rn(a, -b) the compiler hoists the negations of the shared partner pairs into 16 extra
-// FADD per row.
+// tile-relative bin column -> float offset of (column, first row of the pair) inside a pair row
+__device__ __forceinline__ int tcolp(int c_rel) { return SLOTP * (c_rel >> 3) + 2 * (c_rel & 7); }
+
+// a - b on a register pair: sub.f32x2 is one FADD2 with the negate modifier on b (written as
+// __fadd2_rn(a, -b) the compiler hoists the negations of the shared partner pairs into extra FADDs)
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
   unsigned long long ra, rb, rd;
   asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
@@ -307,142 +322,139 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
-__device__ __forceinline__ float2 sqdiff2(float2 t, float2 sgm, float2 r) {
-  const float2 d = sub2(t, sgm);
-  return __ffma2_rn(d, d, r);
-}
-__device__ __forceinline__ float2 sqdiff2_first(float2 t, float2 sgm) {
-  const float2 d = sub2(t, sgm);
-  return __fmul2_rn(d, d);
-}
 
-__device__ __forceinline__ void rowterms3p(const Lane3& L, int ra, int rp, RowT& R) {
-  rp = rp < 0 ? 0 : (rp > ROWS3 - 1 ? ROWS3 - 1 : rp);
-  const float4* pt = reinterpret_cast<const float4*>(L.tile + ra * PITCH3 + L.col_tg);
-  const float4* ps = reinterpret_cast<const float4*>(L.tile + rp * PITCH3 + L.col_seg);
-  const float4 t0 = pt[0], t1 = pt[1];
-  const float4 s0 = ps[0], s1 = ps[1], s2 = ps[3], s3 = ps[4];   // two 12-float column groups
-  const float2 T[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y),
-                       make_float2(t1.z, t1.w)};
-  const float2 To[3] = {make_float2(t0.y, t0.z), make_float2(t0.w, t1.x), make_float2(t1.y, t1.z)};
-  const float2 S2[8] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y),
-                        make_float2(s1.z, s1.w), make_float2(s2.x, s2.y), make_float2(s2.z, s2.w),
-                        make_float2(s3.x, s3.y), make_float2(s3.z, s3.w)};
-  float r[NC3];
+// Row terms of the lane's 9 candidates for the target-side rows (ra, ra + 1), ra even, against the
+// rows (ra + lag, ra + lag + 1): R[c] = (term of row ra, term of row ra + 1).
+__device__ __forceinline__ void rowterms_pair(const Lane3& L, int ra, int lag, float2 (&R)[NC3]) {
+  // partner rows (rp, rp + 1).  rp = -1 is a real case (row ra + 1 against row 0): O's first pair
+  int rp = ra + lag;
+  rp = rp < -1 ? -1 : (rp > ROWS3 - 1 ? ROWS3 - 1 : rp);
+  const float* pe = L.tile + (ra >> 1) * PITCHP + L.col_tg;
+  const float* po = L.tile + ((rp & 1) ? (NPAIR + ((rp + 1) >> 1)) * PITCHP : (rp >> 1) * PITCHP) + L.col_seg;
+  const float4* pt = reinterpret_cast<const float4*>(pe);
+  const float4* ps = reinterpret_cast<const float4*>(po);
+  const float4 t0 = pt[0], t1 = pt[1], t2 = pt[2], t3 = pt[3];
+  const float4 s0 = ps[0], s1 = ps[1], s2 = ps[2], s3 = ps[3];            // bins 0..7 of the segment
+  const float4 s4 = ps[5], s5 = ps[6], s6 = ps[7], s7 = ps[8];            // next column group: bins 8..15
+  const float2 T[8] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y),
+                       make_float2(t1.z, t1.w), make_float2(t2.x, t2.y), make_float2(t2.z, t2.w),
+                       make_float2(t3.x, t3.y), make_float2(t3.z, t3.w)};
+  const float2 Sg[16] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y),
+                         make_float2(s1.z, s1.w), make_float2(s2.x, s2.y), make_float2(s2.z, s2.w),
+                         make_float2(s3.x, s3.y), make_float2(s3.z, s3.w), make_float2(s4.x, s4.y),
+                         make_float2(s4.z, s4.w), make_float2(s5.x, s5.y), make_float2(s5.z, s5.w),
+                         make_float2(s6.x, s6.y), make_float2(s6.z, s6.w), make_float2(s7.x, s7.y),
+                         make_float2(s7.z, s7.w)};
 #pragma unroll
-  for (int m = 0; m < 5; m++) {           // even candidates c = 2m
-    float2 a = sqdiff2_first(T[0], S2[m]);
-    a = sqdiff2(T[1], S2[m + 1], a);
-    a = sqdiff2(T[2], S2[m + 2], a);
-    a = sqdiff2(T[3], S2[m + 3], a);
-    r[2 * m] = a.x + a.y;
+  for (int c = 0; c < NC3; c++) {
+    float2 d = sub2(T[0], Sg[c]);
+    float2 r = __fmul2_rn(d, d);
+#pragma unroll
+    for (int q = 1; q < 8; q++) {
+      d = sub2(T[q], Sg[c + q]);
+      r = __ffma2_rn(d, d, r);
+    }
+    R[c] = r;
   }
-#pragma unroll
-  for (int m = 0; m < 4; m++) {           // odd candidates c = 2m + 1
-    float2 a = sqdiff2_first(To[0], S2[m + 1]);
-    a = sqdiff2(To[1], S2[m + 2], a);
-    a = sqdiff2(To[2], S2[m + 3], a);
-    const float d0 = t0.x - S2[m].y;       // q = 0: partner bin c
-    const float d7 = t1.w - S2[m + 4].x;   // q = 7: partner bin c + 7
-    r[2 * m + 1] = fmaf(d0, d0, a.x) + fmaf(d7, d7, a.y);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) R.p[i] = make_float2(r[2 * i], r[2 * i + 1]);
-  R.s = r[8];
 }
 
-__device__ __forceinline__ RowT rowt_zero() {
-  RowT z;
-#pragma unroll
-  for (int i = 0; i < 4; i++) z.p[i] = make_float2(0.f, 0.f);
-  z.s = 0.f;
-  return z;
-}
-__device__ __forceinline__ RowT rowt_add(const RowT& a, const RowT& b) {
-  RowT o;
-#pragma unroll
-  for (int i = 0; i < 4; i++) o.p[i] = __fadd2_rn(a.p[i], b.p[i]);
-  o.s = a.s + b.s;
-  return o;
-}
-__device__ __forceinline__ void rowt_emit(const Lane3& L, int tau, int dti, const RowT& d, bool edge,
-                                          bool valid) {
-  const float dd[NC3] = {d.p[0].x, d.p[0].y, d.p[1].x, d.p[1].y, d.p[2].x, d.p[2].y, d.p[3].x, d.p[3].y,
-                         d.s};
-  emit_flags3(L, tau, dti, dd, edge, valid);
-}
-
-__device__ __forceinline__ void walk_plain3p(const Lane3& L, int dti, int ta, int tb, bool edge) {
+// ---- a dt that never wraps: delay tree, two rows per iteration ----
+__device__ __forceinline__ void walk_plain_pair(const Lane3& L, int dti, int ta, int tb, bool edge) {
   const int dt = dti - kNlmPast;
-  RowT R1 = rowt_zero(), A[2], B[4];
-  A[0] = A[1] = R1;
-  B[0] = B[1] = B[2] = B[3] = R1;
-  const int steps = tb + 7;
-  for (int i0 = ta; i0 < steps; i0 += 4) {
+  float R1[NC3], A[2][NC3], B[4][NC3];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int i = i0 + u;
-      int ra = 12 + i;                             // tile row of frame t0 - 4 + i
-      ra = ra > ROWS3 - 1 ? ROWS3 - 1 : ra;
-      RowT R0;
-      rowterms3p(L, ra, ra + dt, R0);
-      const RowT a0 = rowt_add(R1, R0);
-      const RowT b0 = rowt_add(A[u & 1], a0);
-      const RowT d = rowt_add(B[u & 3], b0);
-      R1 = R0;
-      A[u & 1] = a0;
-      B[u & 3] = b0;
-      const int tau = i - 7;
-      rowt_emit(L, tau, dti, d, edge, tau >= ta && tau < tb);
+  for (int c = 0; c < NC3; c++) {
+    R1[c] = 0.f;
+    A[0][c] = A[1][c] = 0.f;
+    B[0][c] = B[1][c] = B[2][c] = B[3][c] = 0.f;
+  }
+  // rows i0 .. tb + 6 from an even row (a row before ta only feeds targets before ta), padded to a
+  // multiple of 4 rows; padding rows are clamped into the tile and never emitted
+  const int i0s = ta & ~1;
+  const int steps = tb + 7;
+  for (int i0 = i0s; i0 < steps; i0 += 4) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int i = i0 + 2 * h;
+      int ra = 12 + i;                             // tile row of frame t0 - 4 + i (even)
+      ra = ra > ROWS3 - 2 ? ROWS3 - 2 : ra;
+      float2 R2[NC3];
+      rowterms_pair(L, ra, dt, R2);
+#pragma unroll
+      for (int v = 0; v < 2; v++) {
+        const int u = 2 * h + v;                   // position in the unrolled body: ring indices are static
+        float d[NC3];
+#pragma unroll
+        for (int c = 0; c < NC3; c++) {
+          const float r0 = v ? R2[c].y : R2[c].x;
+          const float a0 = R1[c] + r0;
+          const float b0 = A[u & 1][c] + a0;
+          d[c] = B[u & 3][c] + b0;
+          R1[c] = r0;
+          A[u & 1][c] = a0;
+          B[u & 3][c] = b0;
+        }
+        const int tau = i + v - 7;
+        emit_flags3(L, tau, dti, d, edge, tau >= ta && tau < tb);
+      }
     }
   }
 }
 
-__device__ __forceinline__ void walk_wrap3p(const Lane3& L, int dti, int ta, int tb, bool edge) {
+// ---- a dt whose patch rows wrap through the ring: 8 targets in flight, two rows per iteration ----
+__device__ __forceinline__ void walk_wrap_pair(const Lane3& L, int dti, int ta, int tb, bool edge) {
   const int dt = dti - kNlmPast;
   int rlo = 0, rhi = 8, shift = 0;                   // rows r < rlo or r >= rhi use the alias
   if (dt > 1) { rhi = 9 - dt; shift = -NDT; }        // dt = 2,3,4
   else { rlo = -12 - dt; shift = NDT; }              // dt = -13..-16
-  RowT age[8];
+  float age[8][NC3];
 #pragma unroll
-  for (int r = 0; r < 8; r++) age[r] = rowt_zero();
+  for (int r = 0; r < 8; r++)
+#pragma unroll
+    for (int c = 0; c < NC3; c++) age[r][c] = 0.f;
   const int steps = tb + 7;
 #pragma unroll 1
-  for (int i = ta; i < steps; i++) {
-    const int ra = 12 + i;
-    RowT Rm, Rw;
-    rowterms3p(L, ra, ra + dt, Rm);
-    rowterms3p(L, ra, ra + dt + shift, Rw);
+  for (int i = ta & ~1; i < steps; i += 2) {
+    int ra = 12 + i;
+    ra = ra > ROWS3 - 2 ? ROWS3 - 2 : ra;
+    float2 Rm[NC3], Rw[NC3];
+    rowterms_pair(L, ra, dt, Rm);
+    rowterms_pair(L, ra, dt + shift, Rw);
 #pragma unroll
-    for (int r = 7; r >= 1; r--) {
-      const bool w = (r < rlo) || (r >= rhi);
-      RowT sel;
+    for (int v = 0; v < 2; v++) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) sel.p[k] = make_float2(w ? Rw.p[k].x : Rm.p[k].x, w ? Rw.p[k].y : Rm.p[k].y);
-      sel.s = w ? Rw.s : Rm.s;
-      age[r] = rowt_add(age[r - 1], sel);
+      for (int r = 7; r >= 1; r--) {
+        const bool w = (r < rlo) || (r >= rhi);
+#pragma unroll
+        for (int c = 0; c < NC3; c++)
+          age[r][c] = age[r - 1][c] + (w ? (v ? Rw[c].y : Rw[c].x) : (v ? Rm[c].y : Rm[c].x));
+      }
+#pragma unroll
+      for (int c = 0; c < NC3; c++) age[0][c] = (0 < rlo) ? (v ? Rw[c].y : Rw[c].x) : (v ? Rm[c].y : Rm[c].x);
+      const int tau = i + v - 7;
+      if (tau >= ta && tau < tb) {
+        float d[NC3];
+#pragma unroll
+        for (int c = 0; c < NC3; c++) d[c] = age[7][c];
+        emit_flags3(L, tau, dti, d, edge, true);
+      }
     }
-    {
-      const bool w = 0 < rlo;
-#pragma unroll
-      for (int k = 0; k < 4; k++) age[0].p[k] = make_float2(w ? Rw.p[k].x : Rm.p[k].x, w ? Rw.p[k].y : Rm.p[k].y);
-      age[0].s = w ? Rw.s : Rm.s;
-    }
-    const int tau = i - 7;
-    if (tau >= ta) rowt_emit(L, tau, dti, age[7], edge, true);
   }
 }
 
 // S rows are addressed relative to `first_target_row` (+ chunk-local target index); Wg / Fg are
 // the chunk's scratch: Wg[(target * nfull + block) * WPITCH3 + candidate], Fg[(target * nfull +
 // block) * FW3 + word].
-template <bool PK>
-__global__ void __launch_bounds__(NTH3, 1)
+// PK: packed row walk on the row-interleaved tile (two copies, see above), NW warps.  The scalar
+// form keeps the plain tile.  One CTA per SM in both (shared memory).
+template <bool PK, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
             int targets, int last_row, float h, float* __restrict__ Wg, unsigned* __restrict__ Fg) {
+  constexpr int NTH = NW * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* sp = smem_raw;
-  float* tile = reinterpret_cast<float*>(sp);            sp += SMEM3_TILE;
+  float* tile = reinterpret_cast<float*>(sp);            sp += PK ? SMEMP_TILE : SMEM3_TILE;
   unsigned* flags = reinterpret_cast<unsigned*>(sp);     sp += SMEM3_FLAGS;
   unsigned* gate = reinterpret_cast<unsigned*>(sp);      sp += SMEM3_GATE;
   float* prm = reinterpret_cast<float*>(sp);
@@ -458,16 +470,25 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
   const int lane = threadIdx.x & 31;
 
   // ---- stage rows t0-16 .. t0+nT+3 (clamped to the rows that exist), edge-replicated bins ----
-  for (int e = threadIdx.x; e < ROWS3 * GRP3 * 8; e += NTH3) {
+  for (int e = threadIdx.x; e < ROWS3 * GRP3 * 8; e += NTH) {
     const int r = e / (GRP3 * 8);
     const int c_rel = e - r * (GRP3 * 8);
     int c = c_origin + c_rel;
     c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
     int gr = row_t0 - kNlmPast + r;
     gr = gr > last_row ? last_row : gr;
-    tile[r * PITCH3 + tcol3(c_rel)] = S[(size_t)gr * pitchS + c];
+    const float v = S[(size_t)gr * pitchS + c];
+    if (PK) {
+      const int cp = tcolp(c_rel);
+      tile[(r >> 1) * PITCHP + cp + (r & 1)] = v;                               // E: rows (2m, 2m + 1)
+      tile[(NPAIR + ((r + 1) >> 1)) * PITCHP + cp + ((r + 1) & 1)] = v;         // O: rows (2m - 1, 2m)
+      if (r == 0) tile[NPAIR * PITCHP + cp] = v;                                // O's first pair: (0, 0)
+      if (r == ROWS3 - 1) tile[(NPAIR + NPAIRO - 1) * PITCHP + cp + 1] = v;     // O's last pair: (83, 83)
+    } else {
+      tile[r * PITCH3 + tcol3(c_rel)] = v;
+    }
   }
-  for (int e = threadIdx.x; e < TT3 * NB3 * FW3; e += NTH3) flags[e] = 0u;
+  for (int e = threadIdx.x; e < TT3 * NB3 * FW3; e += NTH) flags[e] = 0u;
   if (threadIdx.x == 0) *next_unit = 0u;
   if (threadIdx.x < NB3) {                              // 1/h_b^2 and 4 h_b^2 per paste block
     float inv, thr;
@@ -479,11 +500,13 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
   // block energy gate per (target, paste block): nlm_filter_avx.c:123-129
   if (threadIdx.x < TT3) {
     unsigned bits = 0u;
-    const float* tr = tile + (kNlmPast + threadIdx.x) * PITCH3;
+    const int r = kNlmPast + threadIdx.x;
     for (int bl = 0; bl < NB3; bl++) {
       float ssum = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; q++) ssum += tr[SLOT3 * (bl + 1) + q];
+      for (int q = 0; q < 8; q++)
+        ssum += PK ? tile[(r >> 1) * PITCHP + SLOTP * (bl + 1) + 2 * q + (r & 1)]
+                   : tile[r * PITCH3 + SLOT3 * (bl + 1) + q];
       if (ssum >= 1e-6f) bits |= 1u << bl;
     }
     gate[threadIdx.x] = bits;
@@ -503,11 +526,12 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
     L.flags = flags + L.bl * FW3;
     L.wstride = nfull * WPITCH3;
     L.wout = Wg + ((size_t)tau0 * nfull + (L.active ? b : 0)) * WPITCH3;
-    L.col_tg = SLOT3 * (L.bl + 1);
-    L.col_seg = SLOT3 * (L.bl + L.g);
+    L.col_tg = (PK ? SLOTP : SLOT3) * (L.bl + 1);
+    L.col_seg = (PK ? SLOTP : SLOT3) * (L.bl + L.g);
     const int bc = 8 * b + 4;
     L.inv = prm[L.bl];
     L.thr = prm[NB3 + L.bl];
+    L.neg1 = fmaf(0.0f, h, -1.0f);
     L.hi_df = K - 1 - bc;
     L.lo_clamp = (b == 0) && (L.g == 0);
     const bool edge = (blk0 == 0) || (blk0 + NB3 >= nfull);
@@ -523,8 +547,8 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
       const int tb = half == 1 ? mid : nT;
       if (ta >= tb) continue;
       if (PK) {
-        if (dti < 4 || dti > 17) walk_wrap3p(L, dti, ta, tb, edge);
-        else walk_plain3p(L, dti, ta, tb, edge);
+        if (dti < 4 || dti > 17) walk_wrap_pair(L, dti, ta, tb, edge);
+        else walk_plain_pair(L, dti, ta, tb, edge);
       } else {
         if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
         else walk_plain3(L, dti, ta, tb, edge);
@@ -535,7 +559,7 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
 
   // ---- bit fields (and the gate) of the tile -> scratch ----
   const int nbv = (nfull - blk0 < NB3) ? nfull - blk0 : NB3;      // valid paste blocks of this tile
-  for (int e = threadIdx.x; e < nT * nbv * FW3; e += NTH3) {
+  for (int e = threadIdx.x; e < nT * nbv * FW3; e += NTH) {
     const int tau = e / (nbv * FW3);
     const int rem = e - tau * (nbv * FW3);
     const int bl = rem / FW3;
@@ -600,343 +624,6 @@ nlm3_paste_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int
 }
 
 
-// Pass 2, second form: 8 lanes per (target, block), lanes over CANDIDATES.  Lane j takes the
-// accepted candidates of rank j, j + 8, ... (rank = position among the set bits of the field,
-// i.e. ascending (dt, df), the self candidate included), requests its weight and its eight
-// pasted values TOGETHER -- 72 loads in flight per pair and round instead of one L2 / DRAM
-// round trip per candidate -- and accumulates eight bin sums; the eight lanes are then added
-// by a transposing butterfly (7 shuffles) that leaves bin j in lane j.  The summation order
-// (per lane by rank, then a fixed tree over lanes) depends only on the pair's own candidate
-// set: deterministic and independent of the tiling, like the first form.
-__device__ __forceinline__ int nth_set_bit(unsigned v, int n) {   // position of the n-th (0-based) set bit
-  int pos = 0, c;
-  c = __popc(v & 0xffffu); if (n >= c) { n -= c; pos += 16; v >>= 16; }
-  c = __popc(v & 0xffu);   if (n >= c) { n -= c; pos += 8;  v >>= 8; }
-  c = __popc(v & 0xfu);    if (n >= c) { n -= c; pos += 4;  v >>= 4; }
-  c = __popc(v & 0x3u);    if (n >= c) { n -= c; pos += 2;  v >>= 2; }
-  if (n >= (int)(v & 1u)) pos += 1;
-  return pos;
-}
-
-__global__ void __launch_bounds__(128)
-nlm3_paste2_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
-                   int targets, const float* __restrict__ Wg, const unsigned* __restrict__ Fg,
-                   float* __restrict__ out, int pitchO) {
-  const int pair = blockIdx.x * 16 + (threadIdx.x >> 3);
-  const int j = threadIdx.x & 7;
-  const unsigned gmask = 0xffu << (threadIdx.x & 24);          // the 8 lanes of this pair
-  if (pair >= targets * nfull) return;                          // whole groups leave together
-  const int tau = pair / nfull;
-  const int b = pair - tau * nfull;
-  const int bs = 8 * b;
-  const float* trow = S + (size_t)(first_target_row + tau) * pitchS;      // frame t
-  const float tv = trow[bs + j];
-  const uint4* fp = reinterpret_cast<const uint4*>(Fg + (size_t)pair * FW3);
-  const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1), f2 = __ldg(fp + 2);
-  unsigned fw[FW3] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
-  float res = tv;
-  if (!((fw[GATED3 >> 5] >> (GATED3 & 31)) & 1u)) {
-    constexpr int kSelf = kNlmPast * 17 + kNlmRangeFreq;        // (dt 0, df 0): always accepted
-    fw[GATED3 >> 5] &= ~(1u << (GATED3 & 31));
-    fw[kSelf >> 5] |= 1u << (kSelf & 31);
-    int cum[FW3 + 1];
-    cum[0] = 0;
-#pragma unroll
-    for (int i = 0; i < FW3; i++) cum[i + 1] = cum[i] + __popc(fw[i]);
-    const int n = cum[FW3];
-    const float w_self = schraudolph_exp3(-0.0f);
-    const float* wp = Wg + (size_t)pair * WPITCH3;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    float ws = 0.f;
-    for (int r0 = 0; r0 < n; r0 += 8) {
-      const int rank = r0 + j;
-      if (rank < n) {
-        unsigned word = fw[0];
-        int base = 0, wi = 0;
-#pragma unroll
-        for (int i = 1; i < FW3; i++)
-          if (rank >= cum[i]) { word = fw[i]; base = cum[i]; wi = i; }
-        const int p = 32 * wi + nth_set_bit(word, rank - base);   // candidate index dti * 17 + dfi
-        const int dti = (p * 241) >> 12;                          // p / 17 for p < 357
-        const int df = p - 17 * dti - kNlmRangeFreq;
-        const float* prow = trow + (ptrdiff_t)(dti - kNlmPast) * pitchS;   // frame t + dt
-        float wgt = (p == kSelf) ? w_self : __ldg(wp + p);
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          int c = bs + i + df;                                    // bin clamp(bs + i + df)
-          c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
-          v[i] = __ldg(prow + c);
-        }
-        if (wgt < kNlmMinWeight) wgt = 0.f;                       // nlm_filter_avx.c:219-221
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = fmaf(wgt, v[i], acc[i]);
-        ws += wgt;
-      }
-    }
-    // transposing butterfly over the 8 lanes of the pair: lane j ends with bin j
-    float a4[4], a2[2], a1;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float send = (j & 4) ? acc[i] : acc[i + 4];
-      const float keep = (j & 4) ? acc[i + 4] : acc[i];
-      a4[i] = keep + __shfl_xor_sync(gmask, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const float send = (j & 2) ? a4[i] : a4[i + 2];
-      const float keep = (j & 2) ? a4[i + 2] : a4[i];
-      a2[i] = keep + __shfl_xor_sync(gmask, send, 2);
-    }
-    {
-      const float send = (j & 1) ? a2[0] : a2[1];
-      const float keep = (j & 1) ? a2[1] : a2[0];
-      a1 = keep + __shfl_xor_sync(gmask, send, 1);
-    }
-    ws += __shfl_xor_sync(gmask, ws, 4);
-    ws += __shfl_xor_sync(gmask, ws, 2);
-    ws += __shfl_xor_sync(gmask, ws, 1);
-    res = (ws > kNlmMinWeight) ? a1 / ws : tv;                    // nlm_filter_avx.c:237-243
-  }
-  out[(size_t)tau * pitchO + bs + j] = res;
-}
-
-
-// =============================================================================================
-// Fused, persistent form (round 2): ONE launch per call.  A CTA per SM takes (target tile, block
-// tile) work items from a global queue -- highest block tiles first, they hold the most accepted
-// candidates -- so there is no chunking and no wave quantisation (the two-pass form ran 442 CTAs
-// = 2.99 waves per chunk of 2176 targets and paid a partial wave plus a kernel boundary per
-// chunk).  The paste is the tile's epilogue: the bit fields never leave shared memory, the pasted
-// values come from the staged tile (its edge-replicated halo is clamp_index), and the weights are
-// read back from a scratch region private to the CTA a few microseconds after they were written,
-// i.e. from L2.  The two-pass form read flags and weights back in a second kernel; by then they
-// had left L2 (ncu, round 1: 123 MB of DRAM reads per chunk at a 32 % L2 hit rate, 6.4 x the
-// algorithmic traffic of the whole NLM), which is what bounded the paste kernel.
-// Paste order per (target, block): lanes over candidates by rank, then a fixed tree over the 8
-// lanes (as nlm3_paste2_kernel): deterministic, independent of tiling and scheduling.
-// =============================================================================================
-template <bool PK, int MAXREG, bool PERSIST>
-__global__ void __maxnreg__(MAXREG)
-nlm4_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
-            int targets, int last_row, float h, float* __restrict__ Wg, unsigned* __restrict__ queue,
-            float* __restrict__ out, int pitchO) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char* sp = smem_raw;
-  float* tile = reinterpret_cast<float*>(sp);            sp += SMEM3_TILE;
-  unsigned* flags = reinterpret_cast<unsigned*>(sp);     sp += SMEM3_FLAGS;
-  unsigned* gate = reinterpret_cast<unsigned*>(sp);      sp += SMEM3_GATE;
-  float* prm = reinterpret_cast<float*>(sp);
-  unsigned* next_unit = reinterpret_cast<unsigned*>(prm + 2 * NB3);
-  unsigned* cur_tile = next_unit + 1;
-
-  const int nbt = (nfull + NB3 - 1) / NB3;               // block tiles
-  const int ntt = (targets + TT3 - 1) / TT3;             // target tiles
-  const int ntiles = nbt * ntt;
-  const int lane = threadIdx.x & 31;
-  // PERSIST: a CTA per SM pulls tiles from the queue.  Otherwise a CTA per tile (the hardware
-  // scheduler hands SMs to the other lanes' kernels as the grid drains) and the weight region is
-  // the SM's: one CTA per SM at a time (124 KB of shared memory each), %smid fixed for its life.
-  unsigned region = blockIdx.x;
-  if (!PERSIST) asm("mov.u32 %0, %%smid;" : "=r"(region));
-  float* Wcta = Wg + (size_t)region * ((size_t)TT3 * NB3 * WPITCH3);
-
-  for (int iter = 0;; iter++) {
-    if (PERSIST) {
-      if (threadIdx.x == 0) *cur_tile = atomicAdd(queue, 1u);
-      __syncthreads();                                   // also: the previous tile's epilogue is done
-    }
-    const int tidx = PERSIST ? (int)*cur_tile : (iter == 0 ? (int)blockIdx.x : ntiles);
-    if (tidx >= ntiles) break;
-    const int bt = nbt - 1 - tidx / ntt;                 // highest block tiles first
-    const int tt = tidx - (tidx / ntt) * ntt;
-    const int blk0 = bt * NB3;
-    const int tau0 = tt * TT3;
-    const int nT = (targets - tau0 < TT3) ? targets - tau0 : TT3;
-    const int row_t0 = first_target_row + tau0;          // S row of target 0 of this tile
-    const int c_origin = blk0 * 8 - 8;
-
-    // ---- stage rows t0-16 .. t0+nT+3 (clamped to the rows that exist), edge-replicated bins ----
-    for (int e = threadIdx.x; e < ROWS3 * GRP3 * 8; e += NTH3) {
-      const int r = e / (GRP3 * 8);
-      const int c_rel = e - r * (GRP3 * 8);
-      int c = c_origin + c_rel;
-      c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
-      int gr = row_t0 - kNlmPast + r;
-      gr = gr > last_row ? last_row : gr;
-      tile[r * PITCH3 + tcol3(c_rel)] = S[(size_t)gr * pitchS + c];
-    }
-    for (int e = threadIdx.x; e < TT3 * NB3 * FW3; e += NTH3) flags[e] = 0u;
-    if (threadIdx.x == 0) *next_unit = 0u;
-    if (threadIdx.x < NB3) {                              // 1/h_b^2 and 4 h_b^2 per paste block
-      float inv, thr;
-      block_params3(8 * (blk0 + threadIdx.x) + 4, K, h, &inv, &thr);
-      prm[threadIdx.x] = inv;
-      prm[NB3 + threadIdx.x] = thr;
-    }
-    __syncthreads();
-    // block energy gate per (target, paste block): nlm_filter_avx.c:123-129
-    if (threadIdx.x < TT3) {
-      unsigned bits = 0u;
-      const float* tr = tile + (kNlmPast + threadIdx.x) * PITCH3;
-      for (int bl = 0; bl < NB3; bl++) {
-        float ssum = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; q++) ssum += tr[SLOT3 * (bl + 1) + q];
-        if (ssum >= 1e-6f) bits |= 1u << bl;
-      }
-      gate[threadIdx.x] = bits;
-    }
-    __syncthreads();
-
-    {
-      Lane3 L;
-      L.tile = tile;
-      L.bl = lane >> 1;
-      L.g = lane & 1;
-      const int b = blk0 + L.bl;
-      L.active = b < nfull;
-      L.live = 0ull;
-      if (L.active)
-        for (int t = 0; t < TT3; t++) L.live |= (unsigned long long)((gate[t] >> L.bl) & 1u) << t;
-      L.flags = flags + L.bl * FW3;
-      L.wstride = NB3 * WPITCH3;
-      L.wout = Wcta + (size_t)L.bl * WPITCH3;
-      L.col_tg = SLOT3 * (L.bl + 1);
-      L.col_seg = SLOT3 * (L.bl + L.g);
-      const int bc = 8 * b + 4;
-      L.inv = prm[L.bl];
-      L.thr = prm[NB3 + L.bl];
-      L.hi_df = K - 1 - bc;
-      L.lo_clamp = (b == 0) && (L.g == 0);
-      const bool edge = (blk0 == 0) || (blk0 + NB3 >= nfull);
-#pragma unroll 1
-      for (;;) {
-        int u = 0;
-        if (lane == 0) u = (int)atomicAdd(next_unit, 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= NUNIT3) break;
-        const int dti = c_units3[u][0], half = c_units3[u][1];
-        const int mid = (nT + 1) >> 1;
-        const int ta = half == 2 ? mid : 0;
-        const int tb = half == 1 ? mid : nT;
-        if (ta >= tb) continue;
-        if (PK) {
-          if (dti < 4 || dti > 17) walk_wrap3p(L, dti, ta, tb, edge);
-          else walk_plain3p(L, dti, ta, tb, edge);
-        } else {
-          if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
-          else walk_plain3(L, dti, ta, tb, edge);
-        }
-      }
-    }
-    __syncthreads();            // every weight of the tile is written, every bit set
-
-    // ---- epilogue: paste the tile ----
-    const int nbv = (nfull - blk0 < NB3) ? nfull - blk0 : NB3;      // valid paste blocks of this tile
-    const int npairs = nT * nbv;
-    const int j = threadIdx.x & 7;
-    const unsigned gmask = 0xffu << (threadIdx.x & 24);             // the 8 lanes of a pair
-    for (int pl = threadIdx.x >> 3; pl < npairs; pl += NTH3 / 8) {
-      const int tau = pl / nbv;
-      const int bl = pl - tau * nbv;
-      const float* trow = tile + (kNlmPast + tau) * PITCH3;         // frame t
-      const int colb = 8 * (bl + 1);                                // tile-relative column of bin bs
-      const float tv = trow[tcol3(colb + j)];
-      float res = tv;
-      if ((gate[tau] >> bl) & 1u) {
-        const unsigned* fpair = flags + (tau * NB3 + bl) * FW3;
-        // most pairs accepted nothing but themselves (the threshold 4 h_b^2 is far below the
-        // SSD of two noise patches): lane j looks at words j and j + 8, one vote decides
-        unsigned mine = fpair[j] | (j < FW3 - 8 ? fpair[j + 8] : 0u);
-        mine |= __shfl_xor_sync(gmask, mine, 4);
-        mine |= __shfl_xor_sync(gmask, mine, 2);
-        mine |= __shfl_xor_sync(gmask, mine, 1);
-        const float w_self = schraudolph_exp3(-0.0f);
-        if (mine == 0u) {
-          // the self candidate alone: acc = w v, wsum = w (w_self > 1e-10)
-          res = fmaf(w_self, tv, 0.f) / w_self;
-        } else {
-        // lanes over candidates by rank (ascending (dt, df), the self candidate included): lane j
-        // takes ranks j, j + 8, ...; weight and the eight pasted values are requested together.
-        // (Tried: lane j walking its own bits {j, j+8, j+16, j+24} of the twelve words without any
-        // ranking -- twelve divergent loops per pair, 1.7 x slower for the whole kernel.)
-        unsigned fw[FW3];
-        const uint4* fp = reinterpret_cast<const uint4*>(fpair);
-        const uint4 f0 = fp[0], f1 = fp[1], f2 = fp[2];
-        fw[0] = f0.x; fw[1] = f0.y; fw[2] = f0.z; fw[3] = f0.w;
-        fw[4] = f1.x; fw[5] = f1.y; fw[6] = f1.z; fw[7] = f1.w;
-        fw[8] = f2.x; fw[9] = f2.y; fw[10] = f2.z; fw[11] = f2.w;
-        constexpr int kSelf = kNlmPast * 17 + kNlmRangeFreq;        // (dt 0, df 0): always accepted
-        fw[kSelf >> 5] |= 1u << (kSelf & 31);
-        int cum[FW3 + 1];
-        cum[0] = 0;
-#pragma unroll
-        for (int i = 0; i < FW3; i++) cum[i + 1] = cum[i] + __popc(fw[i]);
-        const int n = cum[FW3];
-        const float* wp = Wcta + (size_t)(tau * NB3 + bl) * WPITCH3;
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = 0.f;
-        float ws = 0.f;
-        for (int r0 = 0; r0 < n; r0 += 8) {
-          const int rank = r0 + j;
-          if (rank < n) {
-            unsigned word = fw[0];
-            int base = 0, wi = 0;
-#pragma unroll
-            for (int i = 1; i < FW3; i++)
-              if (rank >= cum[i]) { word = fw[i]; base = cum[i]; wi = i; }
-            const int p = 32 * wi + nth_set_bit(word, rank - base);   // candidate index dti * 17 + dfi
-            const int dti = (p * 241) >> 12;                          // p / 17 for p < 357
-            const int c0 = colb + p - 17 * dti - kNlmRangeFreq;       // tile column of bin bs + df
-            float wgt = (p == kSelf) ? w_self : __ldcg(wp + p);       // written by this CTA: L2, not L1
-            const float* prow = trow + (dti - kNlmPast) * PITCH3;     // frame t + dt
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              const int c = c0 + i;                                   // halo column = clamp(bs + i + df)
-              v[i] = prow[c + 4 * (c >> 3)];                          // tcol3(c)
-            }
-            if (wgt < kNlmMinWeight) wgt = 0.f;                       // nlm_filter_avx.c:219-221
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = fmaf(wgt, v[i], acc[i]);
-            ws += wgt;
-          }
-        }
-        // transposing butterfly over the 8 lanes of the pair: lane j ends with bin j
-        float a4[4], a2[2], a1;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float send = (j & 4) ? acc[i] : acc[i + 4];
-          const float keep = (j & 4) ? acc[i + 4] : acc[i];
-          a4[i] = keep + __shfl_xor_sync(gmask, send, 4);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const float send = (j & 2) ? a4[i] : a4[i + 2];
-          const float keep = (j & 2) ? a4[i + 2] : a4[i];
-          a2[i] = keep + __shfl_xor_sync(gmask, send, 2);
-        }
-        {
-          const float send = (j & 1) ? a2[0] : a2[1];
-          const float keep = (j & 1) ? a2[1] : a2[0];
-          a1 = keep + __shfl_xor_sync(gmask, send, 1);
-        }
-        ws += __shfl_xor_sync(gmask, ws, 4);
-        ws += __shfl_xor_sync(gmask, ws, 2);
-        ws += __shfl_xor_sync(gmask, ws, 1);
-        res = (ws > kNlmMinWeight) ? a1 / ws : tv;                  // nlm_filter_avx.c:237-243
-        }
-      }
-      out[(size_t)(tau0 + tau) * pitchO + 8 * (blk0 + bl) + j] = res;
-    }
-    // the loop head's barrier keeps the next tile's staging behind this epilogue
-  }
-}
-
 }  // namespace
 
 // Targets per chunk: close to CHUNK3, and such that the grid of the distance kernel (target tiles
@@ -964,104 +651,49 @@ struct Scratch3 {
   float* W = nullptr;
   unsigned* F = nullptr;
   size_t pairs = 0;
-  bool fused = false;    // sized for the fused kernel (per-CTA regions) rather than per chunk
 };
 static std::mutex g_scratch_mu;
 static std::map<cudaStream_t, Scratch3> g_scratch;
+
+// packed distance kernel: warps per CTA.  The pair walkers keep ~190 registers live (8 ages or the
+// delay tree of 9 candidates, 48 operand registers of a row pair, 18 row terms), which 12 warps
+// cannot have (168 per thread): 8 warps with up to 255 registers.  The 9 independent accumulation
+// chains per lane give the ILP that two warps per scheduler need.
+constexpr int NWP = 8;
 
 bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int targets, float h,
                  float* Shat, cudaStream_t st) {
   const int nfull = g.K / 8;
   if (nfull <= 0 || targets <= 0) return true;
-  // per device and context, hence on every call rather than once per process
-  // measurement knob: SB_NLM_PACKED=0 selects the scalar FADD / FFMA row walk
+  // measurement knob: SB_NLM_PACKED=0 selects the scalar FADD / FFMA row walk (12 warps)
   static const bool packed = [] {
     const char* e = getenv("SB_NLM_PACKED");
     return e ? atoi(e) != 0 : true;
   }();
-  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)SMEM3));
-  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)SMEM3));
-  // measurement knob: SB_NLM_FUSED=0 selects the two-pass form (distance kernel + paste kernel
-  // per chunk of ~2k targets)
-  static const bool fused = [] {
-    const char* e = getenv("SB_NLM_FUSED");
-    return e ? atoi(e) != 0 : true;
+  // per device and context, hence on every call rather than once per process
+  // measurement knob: SB_NLM_WARPS=10 runs the packed kernel with 10 warps (204 registers)
+  static const int pwarps = [] {
+    const char* e = getenv("SB_NLM_WARPS");
+    const int v = e ? atoi(e) : NWP; return (v == 10 || v == 12) ? v : NWP;
   }();
-  if (fused) {
-    // measurement knob: SB_NLM_MAXREG=168 lets the kernel use the whole register file of its SM
-    // (default 128: a quarter of the registers, 100 KB of shared memory and the idle issue slots
-    // of the SM stay available to the kernels of the other lanes)
-    static const int maxreg = [] {
-      const char* e = getenv("SB_NLM_MAXREG");
-      return e ? atoi(e) : 128;
-    }();
-    // measurement knob: SB_NLM_PERSIST=1: a CTA per SM and a tile queue instead of a CTA per tile
-    static const bool persist = [] {
-      const char* e = getenv("SB_NLM_PERSIST");
-      return e ? atoi(e) != 0 : false;
-    }();
-    const void* fn;
-    if (persist)
-      fn = packed ? (maxreg > 128 ? (const void*)nlm4_kernel<true, 168, true> : (const void*)nlm4_kernel<true, 128, true>)
-                  : (maxreg > 128 ? (const void*)nlm4_kernel<false, 168, true> : (const void*)nlm4_kernel<false, 128, true>);
-    else
-      fn = packed ? (maxreg > 128 ? (const void*)nlm4_kernel<true, 168, false> : (const void*)nlm4_kernel<true, 128, false>)
-                  : (maxreg > 128 ? (const void*)nlm4_kernel<false, 168, false> : (const void*)nlm4_kernel<false, 128, false>);
-    SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM3));
-    int dev = 0, sms = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int ntiles = ((nfull + NB3 - 1) / NB3) * ((targets + TT3 - 1) / TT3);
-    const int ctas = persist ? (ntiles < sms ? ntiles : sms) : ntiles;
-    Scratch3 sc;
-    {
-      std::lock_guard<std::mutex> lock(g_scratch_mu);
-      Scratch3& ref = g_scratch[st];
-      // W: one private region of TT3 x NB3 pairs per CTA; F: the tile queue counter
-      const size_t need = (size_t)sms * TT3 * NB3;
-      if (ref.pairs < need || !ref.fused) {
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (ref.W) cudaFree(ref.W);
-        if (ref.F) cudaFree(ref.F);
-        ref = Scratch3();
-        SB_CUDA(cudaMalloc(&ref.W, need * WPITCH3 * sizeof(float)));
-        SB_CUDA(cudaMalloc(&ref.F, 256));
-        ref.pairs = need;
-        ref.fused = true;
-      }
-      sc = ref;
-    }
-    SB_CUDA(cudaMemsetAsync(sc.F, 0, sizeof(unsigned), st));
-    const int last_row = first_target_row + targets - 1 + kNlmFuture;
-    {
-      const float* S_ = S;
-      int pitchS = g.Kp, K_ = g.K, nfull_ = nfull, ftr = first_target_row, tg = targets, lr = last_row;
-      float h_ = h;
-      float* W_ = sc.W;
-      unsigned* Q_ = sc.F;
-      float* out_ = Shat;
-      int pitchO = g.Kp;
-      void* args[] = {&S_, &pitchS, &K_, &nfull_, &ftr, &tg, &lr, &h_, &W_, &Q_, &out_, &pitchO};
-      SB_CUDA(cudaLaunchKernel(fn, dim3(ctas), dim3(NTH3), args, SMEM3, st));
-    }
-    SB_LAUNCH_CHECK();
-    return true;
-  }
+  if (packed) {
+    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true, NWP>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEMP));
+    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true, 10>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEMP));
+    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true, 12>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEMP));
+  } else
+    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<false, NW3>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM3));
   const int chunk = nlm3_chunk_targets(g.K);
-  // measurement knob: SB_NLM_PASTE=1 selects the first paste form (lanes over bins)
-  static const int paste_form = [] {
-    const char* e = getenv("SB_NLM_PASTE");
-    return e ? atoi(e) : 2;
-  }();
   Scratch3 sc;
   {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     Scratch3& ref = g_scratch[st];
     // sized for the largest chunk seen on this stream (small sub-calls keep it small)
     const size_t need = (size_t)(targets < chunk ? targets : chunk) * (size_t)nfull;
-    if (ref.pairs < need || ref.fused) {
+    if (ref.pairs < need) {
       SB_CUDA(cudaStreamSynchronize(st));
       if (ref.W) cudaFree(ref.W);
       if (ref.F) cudaFree(ref.F);
@@ -1077,25 +709,25 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   for (int t0 = 0; t0 < targets; t0 += chunk) {
     const int cnt = targets - t0 < chunk ? targets - t0 : chunk;
     dim3 grid((cnt + TT3 - 1) / TT3, (nfull + NB3 - 1) / NB3);
-    if (packed)
-      nlm3_kernel<true><<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
-                                                   last_row, h, sc.W, sc.F);
+    if (packed && pwarps == 12)
+      nlm3_kernel<true, 12><<<grid, 384, SMEMP, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
+                                                      last_row, h, sc.W, sc.F);
+    else if (packed && pwarps == 10)
+      nlm3_kernel<true, 10><<<grid, 320, SMEMP, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
+                                                      last_row, h, sc.W, sc.F);
+    else if (packed)
+      nlm3_kernel<true, NWP><<<grid, NWP * 32, SMEMP, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0,
+                                                            cnt, last_row, h, sc.W, sc.F);
     else
-      nlm3_kernel<false><<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
-                                                    last_row, h, sc.W, sc.F);
+      nlm3_kernel<false, NW3><<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
+                                                         last_row, h, sc.W, sc.F);
     SB_LAUNCH_CHECK();
     const int pairs = cnt * nfull;
     // (paste on a side stream under the next chunk's distance kernel, two scratch sets: the NLM
     // launch alone 3.5 % faster, the two-lane step unchanged -- the other lane already fills
     // the ramps -- so the scratch stays single)
-    if (paste_form == 1)
-      nlm3_paste_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
-                                                           first_target_row + t0, cnt, h, sc.W, sc.F,
-                                                           Shat + (size_t)t0 * g.Kp, g.Kp);
-    else
-      nlm3_paste2_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull,
-                                                            first_target_row + t0, cnt, sc.W, sc.F,
-                                                            Shat + (size_t)t0 * g.Kp, g.Kp);
+    nlm3_paste_kernel<<<(pairs + 15) / 16, 128, 0, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt, h,
+                                                         sc.W, sc.F, Shat + (size_t)t0 * g.Kp, g.Kp);
     SB_LAUNCH_CHECK();
   }
   return true;
