@@ -33,9 +33,14 @@
 //   of how the targets are tiled, so streaming stays bit-exact.
 //
 // Compiled with -ftz=true (the reference runs NLM under FTZ|DAZ).
+//
+// Round 2 tried and measured, then removed (commit 3e3f1e0 holds the code of
+// the first three): a fused persistent form (one launch per call, paste as the tile's epilogue:
+// -6 % NLM time, the two-lane step slower), a paste with lanes over candidates, two packed FFMA2 /
+// FADD2 forms of the row walk (25 % fewer instructions, same time: the FP32 pipe is what this
+// kernel saturates), and three 4-warp CTAs per SM with the bit fields set in global memory
+// (device-resident +3 %, end to end -1 %).
 #include "sb_common.h"
-
-#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -108,7 +113,6 @@ struct Lane3 {
   bool lo_clamp;          // paste block 0, lower half: df < -4 clamp to centre 0
   bool active;
   float thr, inv;
-  float neg1;             // -1 as a run-time value (SB_NLM_SUB_AS_FMA experiment)
 };
 
 // row terms of the 9 candidates of this lane for target-side row `ra` against row `rp`
@@ -126,11 +130,7 @@ __device__ __forceinline__ void rowterms3(const Lane3& L, int ra, int rp, float 
     float r = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-#ifdef SB_NLM_SUB_AS_FMA
-      const float d = fmaf(seg[c + q], L.neg1, tg[q]);   // experiment: the subtraction on the FFMA path
-#else
       const float d = tg[q] - seg[c + q];
-#endif
       r = fmaf(d, d, r);
     }
     R[c] = r;
@@ -281,180 +281,16 @@ __device__ __forceinline__ void walk_wrap3(const Lane3& L, int dti, int ta, int 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Packed form of the row walk (sm_100a FFMA2 / FADD2: two FP32 operations per issue slot on an
-// aligned register pair; tools/microbench/fp32_pipes.cu: same FLOP rate as FFMA, half the issue
-// slots).  The distance kernel is issue-bound (75 % issue active, FMA pipe 52 %, 66 % of its
-// instructions FADD / FFMA), so halving the FP32 issue slots of the row terms is what is left.
-//
-// The two halves of a register pair are two consecutive ROWS of the tile: the tile is staged
-// row-interleaved, bin c of rows (r, r + 1) side by side, so that an LDS.128 delivers two bins of a
-// row pair and every (target, partner) operand of the packed instructions is an aligned register
-// pair as it comes out of the load -- no shuffling of registers, for any candidate offset.  A lag
-// can be odd, hence two copies of the tile: E pairs rows (2m, 2m + 1), O pairs rows (2m - 1,
-// 2m); the target side always reads E (the walk advances two rows per iteration from an even
-// row), the partner side reads E or O by the parity of row + lag.  The row terms of both rows
-// come out of 8 FADD2 + 8 FFMA2 per candidate (16 + 16 scalar instructions before); the delay tree
-// and the wrapped walker's ages then take the two halves as two ordinary row steps.
-// Per plain row step 99 instead of 171 FP32-pipe issue slots, per wrapped one 288 instead of 432.
-// (A first packed form paired neighbouring BINS: the odd candidates needed a target shifted by
-// one register, and ptxas spent ~45 register moves per row step on pair alignment -- 1 % gain.)
-// ---------------------------------------------------------------------------------------------
-constexpr int SLOTP = 20;                   // floats per column group: 8 bins x 2 rows + 4 pad (80 B apart:
-                                            // a quarter-warp's LDS.128 hit 32 distinct banks)
-constexpr int PITCHP = GRP3 * SLOTP;        // 360 floats per row pair
-constexpr int NPAIR = ROWS3 / 2;            // E: 42 pairs, rows (2m, 2m + 1)
-constexpr int NPAIRO = NPAIR + 1;           // O: 43 pairs, rows (2m - 1, 2m): (-1 -> 0, 0) ... (83, 84 -> 83)
-constexpr size_t SMEMP_TILE = sizeof(float) * (size_t)(NPAIR + NPAIRO) * PITCHP;   // E and O copies
-constexpr size_t SMEMP = SMEMP_TILE + SMEM3_FLAGS + SMEM3_GATE + SMEM3_PRM;
-
-// tile-relative bin column -> float offset of (column, first row of the pair) inside a pair row
-__device__ __forceinline__ int tcolp(int c_rel) { return SLOTP * (c_rel >> 3) + 2 * (c_rel & 7); }
-
-// a - b on a register pair: sub.f32x2 is one FADD2 with the negate modifier on b (written as
-// __fadd2_rn(a, -b) the compiler hoists the negations of the shared partner pairs into extra FADDs)
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-  unsigned long long ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
-
-// Row terms of the lane's 9 candidates for the target-side rows (ra, ra + 1), ra even, against the
-// rows (ra + lag, ra + lag + 1): R[c] = (term of row ra, term of row ra + 1).
-__device__ __forceinline__ void rowterms_pair(const Lane3& L, int ra, int lag, float2 (&R)[NC3]) {
-  // partner rows (rp, rp + 1).  rp = -1 is a real case (row ra + 1 against row 0): O's first pair
-  int rp = ra + lag;
-  rp = rp < -1 ? -1 : (rp > ROWS3 - 1 ? ROWS3 - 1 : rp);
-  const float* pe = L.tile + (ra >> 1) * PITCHP + L.col_tg;
-  const float* po = L.tile + ((rp & 1) ? (NPAIR + ((rp + 1) >> 1)) * PITCHP : (rp >> 1) * PITCHP) + L.col_seg;
-  const float4* pt = reinterpret_cast<const float4*>(pe);
-  const float4* ps = reinterpret_cast<const float4*>(po);
-  const float4 t0 = pt[0], t1 = pt[1], t2 = pt[2], t3 = pt[3];
-  const float4 s0 = ps[0], s1 = ps[1], s2 = ps[2], s3 = ps[3];            // bins 0..7 of the segment
-  const float4 s4 = ps[5], s5 = ps[6], s6 = ps[7], s7 = ps[8];            // next column group: bins 8..15
-  const float2 T[8] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y),
-                       make_float2(t1.z, t1.w), make_float2(t2.x, t2.y), make_float2(t2.z, t2.w),
-                       make_float2(t3.x, t3.y), make_float2(t3.z, t3.w)};
-  const float2 Sg[16] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y),
-                         make_float2(s1.z, s1.w), make_float2(s2.x, s2.y), make_float2(s2.z, s2.w),
-                         make_float2(s3.x, s3.y), make_float2(s3.z, s3.w), make_float2(s4.x, s4.y),
-                         make_float2(s4.z, s4.w), make_float2(s5.x, s5.y), make_float2(s5.z, s5.w),
-                         make_float2(s6.x, s6.y), make_float2(s6.z, s6.w), make_float2(s7.x, s7.y),
-                         make_float2(s7.z, s7.w)};
-#pragma unroll
-  for (int c = 0; c < NC3; c++) {
-    float2 d = sub2(T[0], Sg[c]);
-    float2 r = __fmul2_rn(d, d);
-#pragma unroll
-    for (int q = 1; q < 8; q++) {
-      d = sub2(T[q], Sg[c + q]);
-      r = __ffma2_rn(d, d, r);
-    }
-    R[c] = r;
-  }
-}
-
-// ---- a dt that never wraps: delay tree, two rows per iteration ----
-__device__ __forceinline__ void walk_plain_pair(const Lane3& L, int dti, int ta, int tb, bool edge) {
-  const int dt = dti - kNlmPast;
-  float R1[NC3], A[2][NC3], B[4][NC3];
-#pragma unroll
-  for (int c = 0; c < NC3; c++) {
-    R1[c] = 0.f;
-    A[0][c] = A[1][c] = 0.f;
-    B[0][c] = B[1][c] = B[2][c] = B[3][c] = 0.f;
-  }
-  // rows i0 .. tb + 6 from an even row (a row before ta only feeds targets before ta), padded to a
-  // multiple of 4 rows; padding rows are clamped into the tile and never emitted
-  const int i0s = ta & ~1;
-  const int steps = tb + 7;
-  for (int i0 = i0s; i0 < steps; i0 += 4) {
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int i = i0 + 2 * h;
-      int ra = 12 + i;                             // tile row of frame t0 - 4 + i (even)
-      ra = ra > ROWS3 - 2 ? ROWS3 - 2 : ra;
-      float2 R2[NC3];
-      rowterms_pair(L, ra, dt, R2);
-#pragma unroll
-      for (int v = 0; v < 2; v++) {
-        const int u = 2 * h + v;                   // position in the unrolled body: ring indices are static
-        float d[NC3];
-#pragma unroll
-        for (int c = 0; c < NC3; c++) {
-          const float r0 = v ? R2[c].y : R2[c].x;
-          const float a0 = R1[c] + r0;
-          const float b0 = A[u & 1][c] + a0;
-          d[c] = B[u & 3][c] + b0;
-          R1[c] = r0;
-          A[u & 1][c] = a0;
-          B[u & 3][c] = b0;
-        }
-        const int tau = i + v - 7;
-        emit_flags3(L, tau, dti, d, edge, tau >= ta && tau < tb);
-      }
-    }
-  }
-}
-
-// ---- a dt whose patch rows wrap through the ring: 8 targets in flight, two rows per iteration ----
-__device__ __forceinline__ void walk_wrap_pair(const Lane3& L, int dti, int ta, int tb, bool edge) {
-  const int dt = dti - kNlmPast;
-  int rlo = 0, rhi = 8, shift = 0;                   // rows r < rlo or r >= rhi use the alias
-  if (dt > 1) { rhi = 9 - dt; shift = -NDT; }        // dt = 2,3,4
-  else { rlo = -12 - dt; shift = NDT; }              // dt = -13..-16
-  float age[8][NC3];
-#pragma unroll
-  for (int r = 0; r < 8; r++)
-#pragma unroll
-    for (int c = 0; c < NC3; c++) age[r][c] = 0.f;
-  const int steps = tb + 7;
-#pragma unroll 1
-  for (int i = ta & ~1; i < steps; i += 2) {
-    int ra = 12 + i;
-    ra = ra > ROWS3 - 2 ? ROWS3 - 2 : ra;
-    float2 Rm[NC3], Rw[NC3];
-    rowterms_pair(L, ra, dt, Rm);
-    rowterms_pair(L, ra, dt + shift, Rw);
-#pragma unroll
-    for (int v = 0; v < 2; v++) {
-#pragma unroll
-      for (int r = 7; r >= 1; r--) {
-        const bool w = (r < rlo) || (r >= rhi);
-#pragma unroll
-        for (int c = 0; c < NC3; c++)
-          age[r][c] = age[r - 1][c] + (w ? (v ? Rw[c].y : Rw[c].x) : (v ? Rm[c].y : Rm[c].x));
-      }
-#pragma unroll
-      for (int c = 0; c < NC3; c++) age[0][c] = (0 < rlo) ? (v ? Rw[c].y : Rw[c].x) : (v ? Rm[c].y : Rm[c].x);
-      const int tau = i + v - 7;
-      if (tau >= ta && tau < tb) {
-        float d[NC3];
-#pragma unroll
-        for (int c = 0; c < NC3; c++) d[c] = age[7][c];
-        emit_flags3(L, tau, dti, d, edge, true);
-      }
-    }
-  }
-}
-
 // S rows are addressed relative to `first_target_row` (+ chunk-local target index); Wg / Fg are
 // the chunk's scratch: Wg[(target * nfull + block) * WPITCH3 + candidate], Fg[(target * nfull +
 // block) * FW3 + word].
-// PK: packed row walk on the row-interleaved tile (two copies, see above), NW warps.  The scalar
-// form keeps the plain tile.  One CTA per SM in both (shared memory).
-template <bool PK, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NTH3, 1)
 nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first_target_row,
             int targets, int last_row, float h, float* __restrict__ Wg, unsigned* __restrict__ Fg) {
-  constexpr int NTH = NW * 32;
+  constexpr int NTH = NTH3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* sp = smem_raw;
-  float* tile = reinterpret_cast<float*>(sp);            sp += PK ? SMEMP_TILE : SMEM3_TILE;
+  float* tile = reinterpret_cast<float*>(sp);            sp += SMEM3_TILE;
   unsigned* flags = reinterpret_cast<unsigned*>(sp);     sp += SMEM3_FLAGS;
   unsigned* gate = reinterpret_cast<unsigned*>(sp);      sp += SMEM3_GATE;
   float* prm = reinterpret_cast<float*>(sp);
@@ -477,16 +313,7 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
     c = c < 0 ? 0 : (c > K - 1 ? K - 1 : c);
     int gr = row_t0 - kNlmPast + r;
     gr = gr > last_row ? last_row : gr;
-    const float v = S[(size_t)gr * pitchS + c];
-    if (PK) {
-      const int cp = tcolp(c_rel);
-      tile[(r >> 1) * PITCHP + cp + (r & 1)] = v;                               // E: rows (2m, 2m + 1)
-      tile[(NPAIR + ((r + 1) >> 1)) * PITCHP + cp + ((r + 1) & 1)] = v;         // O: rows (2m - 1, 2m)
-      if (r == 0) tile[NPAIR * PITCHP + cp] = v;                                // O's first pair: (0, 0)
-      if (r == ROWS3 - 1) tile[(NPAIR + NPAIRO - 1) * PITCHP + cp + 1] = v;     // O's last pair: (83, 83)
-    } else {
-      tile[r * PITCH3 + tcol3(c_rel)] = v;
-    }
+    tile[r * PITCH3 + tcol3(c_rel)] = S[(size_t)gr * pitchS + c];
   }
   for (int e = threadIdx.x; e < TT3 * NB3 * FW3; e += NTH) flags[e] = 0u;
   if (threadIdx.x == 0) *next_unit = 0u;
@@ -500,13 +327,11 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
   // block energy gate per (target, paste block): nlm_filter_avx.c:123-129
   if (threadIdx.x < TT3) {
     unsigned bits = 0u;
-    const int r = kNlmPast + threadIdx.x;
+    const float* tr = tile + (kNlmPast + threadIdx.x) * PITCH3;
     for (int bl = 0; bl < NB3; bl++) {
       float ssum = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; q++)
-        ssum += PK ? tile[(r >> 1) * PITCHP + SLOTP * (bl + 1) + 2 * q + (r & 1)]
-                   : tile[r * PITCH3 + SLOT3 * (bl + 1) + q];
+      for (int q = 0; q < 8; q++) ssum += tr[SLOT3 * (bl + 1) + q];
       if (ssum >= 1e-6f) bits |= 1u << bl;
     }
     gate[threadIdx.x] = bits;
@@ -526,12 +351,11 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
     L.flags = flags + L.bl * FW3;
     L.wstride = nfull * WPITCH3;
     L.wout = Wg + ((size_t)tau0 * nfull + (L.active ? b : 0)) * WPITCH3;
-    L.col_tg = (PK ? SLOTP : SLOT3) * (L.bl + 1);
-    L.col_seg = (PK ? SLOTP : SLOT3) * (L.bl + L.g);
+    L.col_tg = SLOT3 * (L.bl + 1);
+    L.col_seg = SLOT3 * (L.bl + L.g);
     const int bc = 8 * b + 4;
     L.inv = prm[L.bl];
     L.thr = prm[NB3 + L.bl];
-    L.neg1 = fmaf(0.0f, h, -1.0f);
     L.hi_df = K - 1 - bc;
     L.lo_clamp = (b == 0) && (L.g == 0);
     const bool edge = (blk0 == 0) || (blk0 + NB3 >= nfull);
@@ -546,13 +370,8 @@ nlm3_kernel(const float* __restrict__ S, int pitchS, int K, int nfull, int first
       const int ta = half == 2 ? mid : 0;
       const int tb = half == 1 ? mid : nT;
       if (ta >= tb) continue;
-      if (PK) {
-        if (dti < 4 || dti > 17) walk_wrap_pair(L, dti, ta, tb, edge);
-        else walk_plain_pair(L, dti, ta, tb, edge);
-      } else {
-        if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
-        else walk_plain3(L, dti, ta, tb, edge);
-      }
+      if (dti < 4 || dti > 17) walk_wrap3(L, dti, ta, tb, edge);
+      else walk_plain3(L, dti, ta, tb, edge);
     }
   }
   __syncthreads();
@@ -632,13 +451,13 @@ int nlm3_chunk_targets(int K) {
   const int nfull = K / 8;
   const int btiles = (nfull + NB3 - 1) / NB3;
   if (btiles <= 0) return CHUNK3;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
-  }
+  static int sms_of[64] = {0};          // per device (handles on several GPUs of one process)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& sms = sms_of[dev & 63];
+  if (sms == 0 &&
+      (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0))
+    sms = 148;
   int waves = (CHUNK3 / TT3 * btiles + sms / 2) / sms;      // nearest whole number of waves
   if (waves < 1) waves = 1;
   int ttiles = waves * sms / btiles;
@@ -655,37 +474,13 @@ struct Scratch3 {
 static std::mutex g_scratch_mu;
 static std::map<cudaStream_t, Scratch3> g_scratch;
 
-// packed distance kernel: warps per CTA.  The pair walkers keep ~190 registers live (8 ages or the
-// delay tree of 9 candidates, 48 operand registers of a row pair, 18 row terms), which 12 warps
-// cannot have (168 per thread): 8 warps with up to 255 registers.  The 9 independent accumulation
-// chains per lane give the ILP that two warps per scheduler need.
-constexpr int NWP = 8;
-
 bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int targets, float h,
                  float* Shat, cudaStream_t st) {
   const int nfull = g.K / 8;
   if (nfull <= 0 || targets <= 0) return true;
-  // measurement knob: SB_NLM_PACKED=0 selects the scalar FADD / FFMA row walk (12 warps)
-  static const bool packed = [] {
-    const char* e = getenv("SB_NLM_PACKED");
-    return e ? atoi(e) != 0 : true;
-  }();
   // per device and context, hence on every call rather than once per process
-  // measurement knob: SB_NLM_WARPS=10 runs the packed kernel with 10 warps (204 registers)
-  static const int pwarps = [] {
-    const char* e = getenv("SB_NLM_WARPS");
-    const int v = e ? atoi(e) : NWP; return (v == 10 || v == 12) ? v : NWP;
-  }();
-  if (packed) {
-    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true, NWP>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEMP));
-    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true, 10>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEMP));
-    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<true, 12>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEMP));
-  } else
-    SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel<false, NW3>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM3));
+  SB_CUDA(cudaFuncSetAttribute((const void*)nlm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)SMEM3));
   const int chunk = nlm3_chunk_targets(g.K);
   Scratch3 sc;
   {
@@ -709,18 +504,8 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   for (int t0 = 0; t0 < targets; t0 += chunk) {
     const int cnt = targets - t0 < chunk ? targets - t0 : chunk;
     dim3 grid((cnt + TT3 - 1) / TT3, (nfull + NB3 - 1) / NB3);
-    if (packed && pwarps == 12)
-      nlm3_kernel<true, 12><<<grid, 384, SMEMP, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
-                                                      last_row, h, sc.W, sc.F);
-    else if (packed && pwarps == 10)
-      nlm3_kernel<true, 10><<<grid, 320, SMEMP, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
-                                                      last_row, h, sc.W, sc.F);
-    else if (packed)
-      nlm3_kernel<true, NWP><<<grid, NWP * 32, SMEMP, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0,
-                                                            cnt, last_row, h, sc.W, sc.F);
-    else
-      nlm3_kernel<false, NW3><<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt,
-                                                         last_row, h, sc.W, sc.F);
+    nlm3_kernel<<<grid, NTH3, SMEM3, st>>>(S, g.Kp, g.K, nfull, first_target_row + t0, cnt, last_row, h,
+                                           sc.W, sc.F);
     SB_LAUNCH_CHECK();
     const int pairs = cnt * nfull;
     // (paste on a side stream under the next chunk's distance kernel, two scratch sets: the NLM

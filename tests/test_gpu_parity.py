@@ -394,27 +394,6 @@ def test_smoke_entry_point(gpu):
     ge.smoke()
 
 
-def test_first_paste_form_still_matches_golden():
-    """SB_NLM_PASTE=1 keeps the first paste kernel (8 lanes over the bins of a pair, candidates
-    walked one after the other) selectable for A/B measurements; it must keep parity, and the
-    default form (lanes over candidates) must agree with it to float rounding."""
-    import os
-    import subprocess
-    import sys
-    from pathlib import Path
-    root = Path(__file__).resolve().parent.parent
-    code = (
-        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "from libspecbleach_b200 import api; from common import load_golden\n"
-        "g = load_golden('nlm_module'); out = api.debug_nlm(g['snr'], float(g['h']))\n"
-        "err = float(np.abs(out[20:] - g['out']).max()); print('ERR', err)\n"
-        "sys.exit(0 if err <= 1e-5 * max(1.0, float(np.abs(g['out']).max())) else 1)\n"
-    ) % (str(root), str(root / "tests"))
-    env = dict(os.environ, SB_NLM_PASTE="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-
-
 def _record(name, payload):
     """measurements made as a side effect of a test, kept for BASELINE.md / DESIGN.md"""
     import json

@@ -14,7 +14,10 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
   float v[NV], s[NV];
 #pragma unroll
-  for (int i = 0; i < NV; i++) { v[i] = (float)(threadIdx.x + i) * 1e-3f; s[i] = (float)i * a; }
+  for (int i = 0; i < NV; i++) {      // opaque values: loaded, so nothing folds into an immediate
+    v[i] = out[(threadIdx.x + 32 * i) & 1023];
+    s[i] = out[(threadIdx.x + 32 * i + 512) & 1023];
+  }
   float ra = a + (float)threadIdx.x * 1e-9f, rb = b + (float)threadIdx.x * 1e-9f;   // registers, not constants
   for (int it = 0; it < ITERS; it++) {
     if (MODE == 0) {            // FFMA with constant-bank operands: v = v*c[a] + c[b]
@@ -28,7 +31,7 @@ __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
       for (int i = 0; i < NV; i++) v[i] = v[i] + ra;
     } else if (MODE == 3) {     // the row-term pattern: d = t - s; r = fma(d, d, r)
 #pragma unroll
-      for (int i = 0; i < NV; i++) { const float d = ra - v[(i + 5) % NV]; s[i] = fmaf(d, d, s[i]); }   // not loop-invariant
+      for (int i = 0; i < NV; i++) { const float d = v[i] - s[i]; s[i] = fmaf(d, d, s[i]); }   // d depends on the accumulator: nothing to hoist
     } else if (MODE == 4) {     // packed: FFMA2 three-register
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
@@ -39,8 +42,7 @@ __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
     } else if (MODE == 5) {     // packed row-term pattern: d2 = t2 - s2 (FADD2 with negated operand), r2 = fma2(d2, d2, r2)
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
-        const int j = (i + 6) % NV;
-        const float2 d = __fadd2_rn(make_float2(ra, rb), make_float2(-v[j], -v[j + 1]));
+        const float2 d = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(-s[i], -s[i + 1]));
         float2 x = __ffma2_rn(d, d, make_float2(s[i], s[i + 1]));
         s[i] = x.x; s[i + 1] = x.y;
       }
