@@ -371,8 +371,6 @@ def class_rooflines(classes: dict, frames: float, w: Workload, hbm_gbs: float, f
         "gain_pre": 20 * Kp,
         "bin_scan": 8 * Kp,
         "final": 32 * Kp + 128,
-        "learn": 4 * Kp + 8 * 4 * Kp,
-        "interp_smooth": 8 * Kp,
         "misc": 4 * Kp,
     }
     out = {}
@@ -406,7 +404,9 @@ def class_rooflines(classes: dict, frames: float, w: Workload, hbm_gbs: float, f
             e.update(bound="fp32", achieved=tf, peak=fp32_tflops, unit="TFLOP/s (direct-form algorithmic)",
                      frac=tf / fp32_tflops if fp32_tflops else None)
         else:
-            e.update(bound="n/a")
+            # learn / finalize / tonal mask / whitening rows: per profile or per learn frame, a
+            # handful of small launches per stream -- no per-frame roofline
+            e.update(bound="n/a (per-profile rows)")
         out[name] = e
     return out
 
@@ -673,6 +673,10 @@ def run_tiled(args):
     if not torch.cuda.is_available() or torch.cuda.device_count() < args.gpus:
         raise SystemExit("bench.py --tiled: not enough CUDA devices -- the product path has no CPU fallback")
     w = Workload(2, 1, 0)
+    if args.file_seconds > 0:          # a longer file amortises the per-tile host work
+        w.seconds = args.file_seconds
+        w.n = int(round(w.seconds * w.sr))
+        w.what = w.what.replace("10 min", f"{w.seconds / 60:.0f} min")
     devices = list(range(args.gpus))
     sb.set_device(0)
     torch.cuda.set_device(0)
@@ -698,9 +702,9 @@ def run_tiled(args):
         for c, d in enumerate(den):
             d.load_parameters(**w.params[c])
         if tiled:
-            for c, d in enumerate(den):
-                d.process_tiled(x_pin[c].array[n_learn:], tiles, args.warmup_frames, devices,
-                                out=y_pin[c].array[n_learn:])
+            if not api.process_tiled_batch(den, [p.array[n_learn:] for p in x_pin],
+                                           [p.array[n_learn:] for p in y_pin], tiles, args.warmup_frames, devices):
+                raise RuntimeError(sb.last_error())
         elif not sb.process_batch(den, [p.array[n_learn:] for p in x_pin], [p.array[n_learn:] for p in y_pin]):
             raise RuntimeError(sb.last_error())
 
@@ -744,8 +748,8 @@ def run_tiled(args):
                               "(CUDA events do not span devices)"),
         "e2e": {"value": vt, "unit": "x realtime", "h2d_bytes_per_step": 2 * n * 4, "d2h_bytes_per_step": 2 * n * 4,
                 "ms_per_step": ms_t / args.steps,
-                "api": "specbleach_b200_process_tiled per channel (page-locked host buffers, tiles dealt to the "
-                       "lanes of every GPU), learn phase through specbleach_b200_process_batch"},
+                "api": "specbleach_b200_process_tiled_batch over both channels (page-locked host buffers, tiles "
+                       "dealt to the lanes of every GPU), learn phase through specbleach_b200_process_batch"},
         "untiled_one_gpu": {"value": v1, "ms_per_step": ms_1 / args.steps,
                             "api": "specbleach_b200_process_batch, same host buffers, device 0"},
         "speedup_over_untiled_one_gpu": vt / v1,
@@ -775,6 +779,8 @@ def main():
                          "process (strong scaling; run WITHOUT torchrun)")
     ap.add_argument("--tiles", type=int, default=0, help="time tiles per channel (0 = one per lane and GPU)")
     ap.add_argument("--warmup-frames", type=int, default=512)
+    ap.add_argument("--file-seconds", type=float, default=0.0,
+                    help="--tiled only: length of the one stereo file (0 = the config's 600 s)")
     ap.add_argument("--lanes", type=int, default=0, help="engine lanes (0 = library default)")
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per sub-call (0 = default)")
     args = ap.parse_args()

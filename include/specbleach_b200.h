@@ -84,6 +84,13 @@ bool specbleach_b200_process_tiled(SpectralBleachHandle instance, uint32_t numbe
                                    uint32_t warmup_frames, const int* devices,
                                    uint32_t device_count, uint32_t flags);
 
+/* The same for several handles at once (the channels of one file): all tiles of all handles are
+ * enqueued before anything is waited for, so tiles of different channels overlap on every GPU. */
+bool specbleach_b200_process_tiled_batch(SpectralBleachHandle* instances, uint32_t count,
+                                         const uint32_t* number_of_samples, const float* const* inputs,
+                                         float* const* outputs, uint32_t tiles, uint32_t warmup_frames,
+                                         const int* devices, uint32_t device_count, uint32_t flags);
+
 /* Strategy branches of the reference that its shipped build never selects.  The
  * reference fixes them at compile time: GAIN_ESTIMATION_TYPE_1D / _2D (configurations.h:195,218),
  * the SuppressionType literal in spectral_denoiser.c:294-297 / spectral_2d_denoiser.c:397-400 and

@@ -65,7 +65,7 @@ EXTENSION_SYMBOLS = ["specbleach_b200_" + n for n in (
     "process_device", "process_batch", "process_batch_device", "profile", "stats_reset",
     "stats_get", "stats_classes", "stats_class_name", "stats_class", "get_geometry",
     "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft", "profile_save", "profile_load",
-    "state_size", "state_save", "state_load", "process_interleaved", "process_tiled", "set_strategy")]
+    "state_size", "state_save", "state_load", "process_interleaved", "process_tiled", "process_tiled_batch", "set_strategy")]
 
 
 def lib():
@@ -146,6 +146,10 @@ def lib():
     L.specbleach_b200_process_tiled.restype = C.c_bool
     L.specbleach_b200_process_tiled.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                                 C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.c_uint32]
+    L.specbleach_b200_process_tiled_batch.restype = C.c_bool
+    L.specbleach_b200_process_tiled_batch.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_uint32),
+                                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32,
+                                                      C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.c_uint32]
     L.specbleach_b200_set_strategy.restype = C.c_bool
     L.specbleach_b200_set_strategy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.specbleach_b200_get_geometry.restype = C.c_bool
@@ -352,6 +356,20 @@ def process_batch(denoisers, inputs, outputs, device: bool = False) -> bool:
         outs = (C.c_void_p * cnt)(*[a.ctypes.data for a in outputs])
         ok = L.specbleach_b200_process_batch(hs, cnt, ns, ins, outs)
     return bool(ok)
+
+
+def process_tiled_batch(denoisers, inputs, outputs, tiles: int, warmup_frames: int = 512, devices=None,
+                        allow_adaptive: bool = False) -> bool:
+    """specbleach_b200_process_tiled_batch over parallel lists of host float32 arrays."""
+    L = lib()
+    cnt = len(denoisers)
+    hs = (C.c_void_p * cnt)(*[d.h for d in denoisers])
+    ns = (C.c_uint32 * cnt)(*[int(a.shape[0]) for a in inputs])
+    ins = (C.c_void_p * cnt)(*[a.ctypes.data for a in inputs])
+    outs = (C.c_void_p * cnt)(*[a.ctypes.data for a in outputs])
+    devs = (C.c_int * len(devices))(*devices) if devices else None
+    return bool(L.specbleach_b200_process_tiled_batch(hs, cnt, ns, ins, outs, int(tiles), int(warmup_frames), devs,
+                                                      len(devices) if devices else 0, 1 if allow_adaptive else 0))
 
 
 PCM_FORMATS = {"f32": 0, "s16": 1, "s24": 2, "s32": 3}

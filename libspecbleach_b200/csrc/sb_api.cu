@@ -235,6 +235,15 @@ bool specbleach_b200_process_tiled(SpectralBleachHandle instance, uint32_t n, co
                            flags);
 }
 
+bool specbleach_b200_process_tiled_batch(SpectralBleachHandle* instances, uint32_t count,
+                                         const uint32_t* number_of_samples, const float* const* inputs,
+                                         float* const* outputs, uint32_t tiles, uint32_t warmup_frames,
+                                         const int* devices, uint32_t device_count, uint32_t flags) {
+  if (!instances || !number_of_samples || !inputs || !outputs || count == 0) return false;
+  return sb::process_tiled_batch(reinterpret_cast<Handle**>(instances), count, number_of_samples, inputs,
+                                 outputs, tiles, warmup_frames, devices, device_count, flags);
+}
+
 bool specbleach_b200_set_strategy(SpectralBleachHandle instance, int gain_type, int suppression_type,
                                   int smoothing_type) {
   if (!instance) return false;

@@ -868,97 +868,126 @@ static void release_tile_handle(Handle* t) {
   g_tile_pool[TilePoolKey{t->device, t->geo, t->two_d}].push_back(t);
 }
 
-bool process_tiled(Handle* h, uint32_t n, const float* in, float* out, uint32_t tiles,
-                   uint32_t warmup_frames, const int* devices, uint32_t device_count, uint32_t flags) {
+// One call for several handles (the channels of a file): every handle's samples are cut into
+// `tiles` tiles, ALL tiles are enqueued before anything is waited for, so the tiles of different
+// channels overlap on the lanes of each GPU and the single host thread pays one synchronisation.
+bool process_tiled_batch(Handle** hs, uint32_t count, const uint32_t* ns, const float* const* ins,
+                         float* const* outs, uint32_t tiles, uint32_t warmup_frames, const int* devices,
+                         uint32_t device_count, uint32_t flags) {
   std::lock_guard<std::recursive_mutex> engine_lock(g_engine_mu);
   DeviceGuard restore_device;
-  if (h->prm.learn_noise > 0 || !h->params_loaded) {
-    set_error_msg("specbleach_b200_process_tiled: the handle must be in denoise mode (load_parameters with learn_noise = 0)");
-    return false;
-  }
-  if (h->prm.adaptive && !(flags & 1u)) {
-    set_error_msg("specbleach_b200_process_tiled: adaptive noise estimation is only approximated by time "
-                  "tiles; pass SPECBLEACH_B200_TILED_ALLOW_ADAPTIVE to accept that");
-    return false;
-  }
-  const GeoK& g = h->geo->k;
-  const uint32_t hop = (uint32_t)g.hop;
-  const uint32_t first = (hop - h->carry) % hop;          // first frame boundary of the stream inside this call
-  const uint32_t frames = n > first ? (n - first) / hop : 0;
-  if (tiles > frames / 64) tiles = frames / 64;           // tiles shorter than 64 frames are pointless
-  if (tiles <= 1) return process_call(h, n, in, out, false);
-  if ((in <= out && out < in + n) || (out <= in && in < out + n)) {
-    // a tile's warm-up input is the previous tile's output region: not in place
-    set_error_msg("specbleach_b200_process_tiled: input and output must not overlap");
-    return false;
-  }
-  SB_CUDA(cudaSetDevice(h->device));
-  Lane* L0 = get_lane(0, g);
-  if (!L0) return false;
-  if (!finalize_profiles(h, L0->stream)) return false;    // the clones take the refined profile
-  // page-locked buffers are DMA'd by every device; pageable ones are registered for the call
-  bool reg_in = false, reg_out = false;
-  if (!is_device_or_pinned(in)) {
-    if (cudaHostRegister(const_cast<float*>(in), (size_t)n * sizeof(float), cudaHostRegisterPortable) == cudaSuccess)
-      reg_in = true;
-    else cudaGetLastError();
-  }
-  if (out != in && !is_device_or_pinned(out)) {
-    if (cudaHostRegister(out, (size_t)n * sizeof(float), cudaHostRegisterPortable) == cudaSuccess) reg_out = true;
-    else cudaGetLastError();
-  }
   struct Tile { uint32_t in_lo, out_lo, out_hi; Handle* h; int device; Lane* lane; };
-  std::vector<Tile> plan;
-  for (uint32_t i = 0; i < tiles; i++) {
-    const uint32_t base = frames / tiles, extra = frames % tiles;
-    const uint32_t lo_f = i * base + (i < extra ? i : extra);
-    const uint32_t hi_f = lo_f + base + (i < extra ? 1u : 0u);
-    Tile t;
-    t.out_lo = i == 0 ? 0u : first + lo_f * hop;
-    t.out_hi = i == tiles - 1 ? n : first + hi_f * hop;
-    t.in_lo = t.out_lo;
-    t.h = nullptr;
-    t.device = h->device;
-    t.lane = nullptr;
-    if (i > 0) {
-      const uint64_t back = (uint64_t)warmup_frames * hop;
-      if ((uint64_t)(t.out_lo - first) < back) {
-        // its warm-up would reach before the call: tile 0 (the exact continuation) absorbs it
-        plan[0].out_hi = t.out_hi;
-        continue;
-      }
-      t.in_lo = t.out_lo - (uint32_t)back;
+  struct Job {
+    Handle* h; uint32_t n; const float* in; float* out;
+    std::vector<Tile> plan;
+    bool reg_in = false, reg_out = false, plain = false;
+  };
+  std::vector<Job> jobs(count);
+  for (uint32_t c = 0; c < count; c++) {
+    Handle* h = hs[c];
+    if (!h || !ins[c] || !outs[c] || ns[c] == 0) {
+      set_error_msg("specbleach_b200_process_tiled: NULL handle / buffer or zero samples");
+      return false;
     }
-    plan.push_back(t);
+    if (h->prm.learn_noise > 0 || !h->params_loaded) {
+      set_error_msg("specbleach_b200_process_tiled: the handle must be in denoise mode (load_parameters with learn_noise = 0)");
+      return false;
+    }
+    if (h->prm.adaptive && !(flags & 1u)) {
+      set_error_msg("specbleach_b200_process_tiled: adaptive noise estimation is only approximated by time "
+                    "tiles; pass SPECBLEACH_B200_TILED_ALLOW_ADAPTIVE to accept that");
+      return false;
+    }
+    for (uint32_t d = 0; d < c; d++)
+      if (hs[d] == h) {
+        set_error_msg("specbleach_b200_process_tiled_batch: a handle appears twice");
+        return false;
+      }
+    Job& J = jobs[c];
+    J.h = h; J.n = ns[c]; J.in = ins[c]; J.out = outs[c];
+    const uint32_t n = J.n;
+    const GeoK& g = h->geo->k;
+    const uint32_t hop = (uint32_t)g.hop;
+    const uint32_t first = (hop - h->carry) % hop;        // first frame boundary of the stream inside this call
+    const uint32_t frames = n > first ? (n - first) / hop : 0;
+    uint32_t nt = tiles;
+    if (nt > frames / 64) nt = frames / 64;               // tiles shorter than 64 frames are pointless
+    if (nt <= 1) { J.plain = true; continue; }
+    if ((J.in <= J.out && J.out < J.in + n) || (J.out <= J.in && J.in < J.out + n)) {
+      // a tile's warm-up input is the previous tile's output region: not in place
+      set_error_msg("specbleach_b200_process_tiled: input and output must not overlap");
+      return false;
+    }
+    for (uint32_t i = 0; i < nt; i++) {
+      const uint32_t base = frames / nt, extra = frames % nt;
+      const uint32_t lo_f = i * base + (i < extra ? i : extra);
+      const uint32_t hi_f = lo_f + base + (i < extra ? 1u : 0u);
+      Tile t;
+      t.out_lo = i == 0 ? 0u : first + lo_f * hop;
+      t.out_hi = i == nt - 1 ? n : first + hi_f * hop;
+      t.in_lo = t.out_lo;
+      t.h = nullptr;
+      t.device = h->device;
+      t.lane = nullptr;
+      if (i > 0) {
+        const uint64_t back = (uint64_t)warmup_frames * hop;
+        if ((uint64_t)(t.out_lo - first) < back) {
+          // its warm-up would reach before the call: tile 0 (the exact continuation) absorbs it
+          J.plan[0].out_hi = t.out_hi;
+          continue;
+        }
+        t.in_lo = t.out_lo - (uint32_t)back;
+      }
+      J.plan.push_back(t);
+    }
   }
   bool ok = true;
-  const size_t nt = plan.size();
-  const int nlanes = ctx().num_lanes;
-  for (size_t i = 0; i < nt && ok; i++) {
-    Tile& t = plan[i];
-    // the last tile stays on the caller's device: its state becomes the caller's
-    if (i > 0) t.device = (devices && device_count && i != nt - 1) ? devices[i % device_count] : h->device;
-    if (cudaSetDevice(t.device) != cudaSuccess) { ok = false; break; }
-    // tiles of one device go round its lanes (i / device_count: consecutive tiles sit on
-    // different devices)
-    const size_t per_dev = (devices && device_count) ? i / device_count : i;
-    t.lane = get_lane((int)(per_dev % (size_t)nlanes), g);
-    if (!t.lane) { ok = false; break; }
-    if (i == 0) {
-      t.h = h;
-    } else {
-      t.h = clone_for_tile(h, t.device, t.lane->stream);
-      if (!t.h) { ok = false; break; }
+  // the clones take the refined profile; page-locked buffers are DMA'd by every device, pageable
+  // ones are registered for the call
+  for (Job& J : jobs) {
+    if (!ok) break;
+    if (J.plain) continue;
+    if (cudaSetDevice(J.h->device) != cudaSuccess) { ok = false; break; }
+    Lane* L0 = get_lane(0, J.h->geo->k);
+    if (!L0 || !finalize_profiles(J.h, L0->stream)) { ok = false; break; }
+    if (!is_device_or_pinned(J.in)) {
+      if (cudaHostRegister(const_cast<float*>(J.in), (size_t)J.n * sizeof(float), cudaHostRegisterPortable) == cudaSuccess)
+        J.reg_in = true;
+      else cudaGetLastError();
     }
-    ok = enqueue_call(t.h, *t.lane, t.out_hi - t.in_lo, in + t.in_lo, out + t.in_lo, false,
-                      t.out_lo - t.in_lo);
+    if (!is_device_or_pinned(J.out)) {
+      if (cudaHostRegister(J.out, (size_t)J.n * sizeof(float), cudaHostRegisterPortable) == cudaSuccess) J.reg_out = true;
+      else cudaGetLastError();
+    }
+  }
+  const int nlanes = ctx().num_lanes;
+  std::map<int, size_t> next_lane;                        // per device: tiles go round its lanes
+  for (Job& J : jobs) {
+    if (!ok) break;
+    if (J.plain) continue;
+    const size_t nt = J.plan.size();
+    for (size_t i = 0; i < nt && ok; i++) {
+      Tile& t = J.plan[i];
+      // tile 0 continues the handle on its own device; the others go round the listed devices
+      if (i > 0 && devices && device_count) t.device = devices[i % device_count];
+      if (cudaSetDevice(t.device) != cudaSuccess) { ok = false; break; }
+      t.lane = get_lane((int)(next_lane[t.device]++ % (size_t)nlanes), J.h->geo->k);
+      if (!t.lane) { ok = false; break; }
+      if (i == 0) {
+        t.h = J.h;
+      } else {
+        t.h = clone_for_tile(J.h, t.device, t.lane->stream);
+        if (!t.h) { ok = false; break; }
+      }
+      ok = enqueue_call(t.h, *t.lane, t.out_hi - t.in_lo, J.in + t.in_lo, J.out + t.in_lo, false,
+                        t.out_lo - t.in_lo);
+    }
   }
   for (auto& dl : ctx().lanes) {
     if (cudaSetDevice(dl.first) != cudaSuccess) continue;
     for (Lane& L : dl.second)
       if (L.stream) cudaStreamSynchronize(L.stream);
   }
-  cudaSetDevice(h->device);
   if (ok) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -966,13 +995,35 @@ bool process_tiled(Handle* h, uint32_t n, const float* in, float* out, uint32_t 
       ok = false;
     }
   }
-  after_sync(h);
-  if (ok && nt > 1) std::swap(*h, *plan[nt - 1].h);       // same device, same geometry: the stream goes on from here
-  for (size_t i = 1; i < nt; i++)
-    if (plan[i].h) release_tile_handle(plan[i].h);
-  if (reg_in) cudaHostUnregister(const_cast<float*>(in));
-  if (reg_out) cudaHostUnregister(out);
+  for (Job& J : jobs) {
+    if (J.plain) continue;
+    const size_t nt = J.plan.size();
+    after_sync(J.h);
+    // the stream goes on from the last tile's state: same device -> the two handles trade places;
+    // another device -> its state travels as a snapshot blob (~0.5 MB)
+    if (ok && nt > 1 && J.plan[nt - 1].h) {
+      Handle* last = J.plan[nt - 1].h;
+      if (last->device == J.h->device) {
+        std::swap(*J.h, *last);
+      } else {
+        std::vector<unsigned char> blob(state_size(last));
+        ok = state_save(last, blob.data(), blob.size()) && state_load(J.h, blob.data(), blob.size());
+      }
+    }
+    for (size_t i = 1; i < nt; i++)
+      if (J.plan[i].h) release_tile_handle(J.plan[i].h);
+    if (J.reg_in) cudaHostUnregister(const_cast<float*>(J.in));
+    if (J.reg_out) cudaHostUnregister(J.out);
+  }
+  // handles too short to tile: the ordinary call
+  for (Job& J : jobs)
+    if (ok && J.plain) ok = process_call(J.h, J.n, J.in, J.out, false);
   return ok;
+}
+
+bool process_tiled(Handle* h, uint32_t n, const float* in, float* out, uint32_t tiles,
+                   uint32_t warmup_frames, const int* devices, uint32_t device_count, uint32_t flags) {
+  return process_tiled_batch(&h, 1, &n, &in, &out, tiles, warmup_frames, devices, device_count, flags);
 }
 
 bool stats_collect(Context& c) {

@@ -47,7 +47,15 @@ bool process_batch(Handle** hs, uint32_t count, const uint32_t* n, const float* 
                    float* const* out, bool device_io);
 bool process_tiled(Handle* h, uint32_t n, const float* in, float* out, uint32_t tiles,
                    uint32_t warmup_frames, const int* devices, uint32_t device_count, uint32_t flags);
+bool process_tiled_batch(Handle** hs, uint32_t count, const uint32_t* ns, const float* const* ins,
+                         float* const* outs, uint32_t tiles, uint32_t warmup_frames, const int* devices,
+                         uint32_t device_count, uint32_t flags);
 bool stats_collect(Context& c);
+
+// sb_io.cu: the streaming state of a handle as one host blob
+size_t state_size(Handle* h);
+bool state_save(Handle* h, void* blob, size_t bytes);
+bool state_load(Handle* h, const void* blob, size_t bytes);
 
 // sb_geometry.cu: private geometry for the FFT-only debug entry point
 Geometry* make_fft_geometry(int fft_size);

@@ -43,6 +43,7 @@
 #include "sb_common.h"
 
 #include <map>
+#include <utility>
 #include <mutex>
 
 namespace sb {
@@ -472,7 +473,8 @@ struct Scratch3 {
   size_t pairs = 0;
 };
 static std::mutex g_scratch_mu;
-static std::map<cudaStream_t, Scratch3> g_scratch;
+// keyed by (device, stream): the legacy default stream is the same handle on every device
+static std::map<std::pair<int, cudaStream_t>, Scratch3> g_scratch;
 
 bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int targets, float h,
                  float* Shat, cudaStream_t st) {
@@ -485,7 +487,9 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
   Scratch3 sc;
   {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    Scratch3& ref = g_scratch[st];
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    Scratch3& ref = g_scratch[std::make_pair(dev, st)];
     // sized for the largest chunk seen on this stream (small sub-calls keep it small)
     const size_t need = (size_t)(targets < chunk ? targets : chunk) * (size_t)nfull;
     if (ref.pairs < need) {

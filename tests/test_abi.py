@@ -137,7 +137,7 @@ def test_launch_share_summary_reads_the_committed_ncu_list():
     """tools/ncu_summary.py --launches is what turns the ncu launch list under profiles/ into
     the share table DESIGN.md quotes; the committed pair must stay consistent."""
     import sys
-    lists = sorted((ROOT / "profiles").glob("r01*_launches_ncu.csv"))
+    lists = sorted((ROOT / "profiles").glob("r0*_launches_ncu.csv"))
     assert lists, "no launch list under profiles/"
     csv_path = lists[-1]
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), "--launches", str(csv_path), "cmd"],
@@ -149,6 +149,37 @@ def test_launch_share_summary_reads_the_committed_ncu_list():
     assert abs(sum(shares.values()) - 100.0) < 1.0
     committed = (ROOT / "profiles" / csv_path.name.replace("launches_ncu.csv", "launch_shares.txt")).read_text()
     assert f"{shares['nlm3_kernel']:.1f}%" in committed
+
+
+def test_bench_line_kernel_shares_agree_with_the_ncu_launch_list():
+    """north_star: every kernel reported against its roofline.  The committed config-2 bench line
+    (profiles/r02_bench_config2.json: roofline_by_class from CUDA events around every launch) and
+    the committed ncu launch list of the same command are two independent measurements of where the
+    step goes; the NLM share and the order of the big classes must agree (ncu's per-launch times are
+    cold-cache and serialised: shares, not absolutes)."""
+    import json
+    import sys
+    line = json.loads((ROOT / "profiles" / "r02_bench_config2.json").read_text().strip().splitlines()[-1])
+    by_class = line["roofline_by_class"]
+    for name in ("forward_fft", "inverse_fft", "nlm", "snr", "gain_pre", "final", "band", "nmr", "ola"):
+        e = by_class[name]
+        assert e["bound"] in ("hbm", "fp32", "smem/fp32", "mufu") and 0.0 < e["frac"] < 2.0, (name, e)
+    ev = {k: v["ms"] for k, v in by_class.items()}
+    ev_total = sum(ev.values())
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), "--launches",
+                        str(ROOT / "profiles" / "r02_launches_ncu.csv"), "cmd"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.splitlines()[2:] if ln.strip()]
+    ncu = {row[0]: float(row[-4].rstrip("%")) for row in rows}
+    ncu_nlm = ncu["nlm3_kernel"] + ncu["nlm3_paste_kernel"]
+    ev_nlm = 100.0 * ev["nlm"] / ev_total
+    assert abs(ncu_nlm - ev_nlm) < 8.0, (ncu_nlm, ev_nlm)
+    assert abs((ncu["forward_kernel<1>"] + ncu["inverse_kernel<1>"]) -
+               100.0 * (ev["forward_fft"] + ev["inverse_fft"]) / ev_total) < 4.0
+    # the NLM roofline object: algorithmic rate above the FP32 peak only through row-SSD sharing
+    rf = line["roofline"]
+    assert rf["bound"] == "fp32" and 0.9 < rf["frac"] < 1.5 and rf["traffic"] > 0
+    assert 0.25 < rf["executed"]["frac_of_peak"] < 0.45
 
 
 def test_library_identity_matches_the_reference_install():

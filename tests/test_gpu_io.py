@@ -358,18 +358,56 @@ def test_c_abi_tiled_call_adaptive_is_an_approximation(gpu, ref):
         (out / "tiled_adaptive_error.json").write_text(json.dumps(res, indent=1))
 
 
+def test_c_abi_tiled_batch_of_two_channels(gpu):
+    """specbleach_b200_process_tiled_batch: both channels of a file in one call (all tiles enqueued
+    before anything is waited for) == one tiled call per channel == the monolithic calls."""
+    from libspecbleach_b200 import api
+    sr = 48000
+    xs = [synth(40.0, sr, 90 + c) for c in range(2)]
+
+    def start():
+        ds = [gpu.Denoiser2D(sr, 50.0) for _ in xs]
+        heads = []
+        for d, x in zip(ds, xs):
+            d.load_parameters(learn_noise=1)
+            heads.append(d.process(x[:sr]))
+            d.load_parameters(**P2D)
+        return ds, heads
+
+    ds, _ = start()
+    mono = [d.process(x[sr:]) for d, x in zip(ds, xs)]
+    ds, _ = start()
+    outs = [np.empty_like(x[sr:]) for x in xs]
+    assert api.process_tiled_batch(ds, [np.ascontiguousarray(x[sr:]) for x in xs], outs, tiles=4)
+    for a, b in zip(mono, outs):
+        assert np.array_equal(a, b)
+    # the handles go on from the last tiles' states
+    tail = synth(2.0, sr, 99)
+    ds2, _ = start()
+    for d, x in zip(ds2, xs):
+        d.process(x[sr:])
+    for d, e in zip(ds, ds2):
+        assert np.array_equal(d.process(tail), e.process(tail))
+
+
 def test_c_abi_tiled_call_across_two_devices(gpu):
-    """tiles dealt to the lanes of two GPUs of one process: bit-identical to one GPU."""
+    """tiles dealt to the lanes of two GPUs of one process: bit-identical to one GPU, and the
+    stream continues from the last tile's state even when that tile ran on the other GPU (the
+    state travels as a snapshot blob)."""
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs")
     sr = 48000
     x = synth(60.0, sr, 89)
+    tail = synth(2.0, sr, 98)
 
-    def run(devices):
+    def run(devices, tiles):
         d = gpu.Denoiser2D(sr, 50.0)
         d.load_parameters(learn_noise=1)
         a = d.process(x[:sr])
         d.load_parameters(**P2D)
-        return np.concatenate([a, d.process_tiled(x[sr:], tiles=8, warmup_frames=512, devices=devices)])
+        b = d.process_tiled(x[sr:], tiles=tiles, warmup_frames=512, devices=devices)
+        return np.concatenate([a, b, d.process(tail)])
 
-    assert np.array_equal(run(None), run([0, 1]))
+    want = run(None, 8)
+    assert np.array_equal(want, run([0, 1], 8))        # last tile (index 7) on device 1
+    assert np.array_equal(want, run([0, 1], 7))        # last tile (index 6) on device 0
