@@ -326,6 +326,10 @@ __device__ __forceinline__ float pre_one(const PreArgs& a, float refv, float n, 
   return al;
 }
 
+// SUP: where alpha comes from -- 0: per bin in pre_one (Berouti, or none), 1: one per band
+// (sup_band_kernel), 2: one per bin from sup_alpha_kernel.  A template so that the shipped
+// strategy keeps its instruction count.
+template <int SUP>
 __global__ void __launch_bounds__(512)
 gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
                 const float* __restrict__ noise_t, const float* __restrict__ mask,
@@ -334,9 +338,6 @@ gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
   const int i = a.first_active + blockIdx.x;
   const size_t ro = (size_t)i * g.Kp;
   const bool tonal = !(a.tonal_gain >= 0.999f);
-  // strategies 1 / 2: one alpha per band (sup_band_kernel); 3: one per bin (sup_alpha_kernel)
-  const bool per_band = a.suppression == 1 || a.suppression == 2;
-  const bool per_bin = a.suppression == 3;
   const float* __restrict__ mrow = mask + (size_t)i * a.mask_stride;
   for (int k = 4 * threadIdx.x; k < g.Kp; k += 4 * blockDim.x) {
     const float4 r4 = ld4(ref + ro + k), n4 = ld4(noise_t + ro + k);
@@ -348,8 +349,8 @@ gain_pre_kernel(const GeoK g, PreArgs a, const float* __restrict__ ref,
         const float m = tonal ? mrow[k + u] : 0.f;
         mg[u] = 0.f; cl[u] = 0.f;
         float alb = 1.f;
-        if (per_band) alb = sup_alpha[(size_t)i * kBandPitch + __ldg(&g.band_of_bin[k + u])];
-        else if (per_bin) alb = sup_alpha[ro + k + u];
+        if (SUP == 1) alb = sup_alpha[(size_t)i * kBandPitch + __ldg(&g.band_of_bin[k + u])];
+        else if (SUP == 2) alb = sup_alpha[ro + k + u];
         al[u] = pre_one(a, rv[u], nv[u], m, &mg[u], &cl[u], alb);
       } else {
         al[u] = 1.f; mg[u] = 0.f; cl[u] = 0.f;
@@ -1216,8 +1217,8 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
       if (a.two_d) {
         PreArgs p0 = pa;
         p0.suppression = 4;                           // alpha is recomputed afterwards
-        gain_pre_kernel<<<active, row_threads(g), 0, st>>>(g, p0, refspec, L.noise, a.mask, L.Mg, L.alpha,
-                                                           L.stable, nullptr);
+        gain_pre_kernel<0><<<active, row_threads(g), 0, st>>>(g, p0, refspec, L.noise, a.mask, L.Mg, L.alpha,
+                                                              L.stable, nullptr);
         SB_LAUNCH_CHECK();
       } else {
         cleanp = L.Mg;                                // 1D: Mg is only written by the smoother later
@@ -1238,8 +1239,16 @@ bool launch_gain_chain(const GeoK& g, const GainArgs& a, Lane& L, Handle& h, cud
     }
     {
       KTimer kt_(kcGainPre, st);
-    gain_pre_kernel<<<active, row_threads(g), 0, st>>>(g, pa, refspec, L.noise, a.mask, L.Mg,
-                                          L.alpha, L.stable, sup_alpha);
+    const int sup = a.suppression_type;
+    if (sup == 1 || sup == 2)
+      gain_pre_kernel<1><<<active, row_threads(g), 0, st>>>(g, pa, refspec, L.noise, a.mask, L.Mg, L.alpha,
+                                                            L.stable, sup_alpha);
+    else if (sup == 3)
+      gain_pre_kernel<2><<<active, row_threads(g), 0, st>>>(g, pa, refspec, L.noise, a.mask, L.Mg, L.alpha,
+                                                            L.stable, sup_alpha);
+    else
+      gain_pre_kernel<0><<<active, row_threads(g), 0, st>>>(g, pa, refspec, L.noise, a.mask, L.Mg, L.alpha,
+                                                            L.stable, sup_alpha);
     SB_LAUNCH_CHECK();
     }
     if (use_veto || !a.two_d) {

@@ -36,8 +36,12 @@ def job_throughput(local_units_seconds: float, local_ms: float, dist=None, devic
 
 # ---------------------------------------------------------------------------
 # N3: one long stream cut into time tiles that run on different
-# handles / GPUs.  A tile starts `warmup_frames` hops early on a fresh handle that
-# was given the finalised noise profile; the warm-up output is thrown away.  What a
+# handles / GPUs.  The product path for this is the C ABI's specbleach_b200_process_tiled[_batch]
+# (tiles over the lanes and GPUs of ONE process, csrc/sb_engine.cu); the helpers below are the
+# host-side counterpart for ranks that are separate processes (one per GPU): the same tile plan,
+# the profile handed over as four small arrays.
+# A tile starts `warmup_frames` hops early on a fresh handle that was given the
+# finalised noise profile; the warm-up output is thrown away.  What a
 # handle carries between frames forgets its start geometrically:
 # the 21-frame NLM ring and the 4-frame delay line are exact after 25 frames, the
 # veto EMAs (0.5 per frame) after ~150, the forward-masking recursion (<= 0.91 per
