@@ -14,7 +14,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 
 namespace sb {
 
@@ -605,11 +608,11 @@ static bool enqueue_host_sub(Handle* h, Lane& L, uint32_t m, const float* src, f
 
 // Pageable caller buffers (what a program written against the reference passes to
 // specbleach[_2d]_process: examples/denoiser_demo.c:217-300): the call is cut into sub-calls of a
-// quarter of the lane's capacity, each copied by THIS thread into one of two page-locked bounce
-// buffers of the lane and handed to the same pipeline; its output comes back through two more.
-// The host copies of sub-call k run while the GPU works on k-1, so the call costs
-// max(host copies, kernels) instead of their sum.  in == out is fine: output k-2 is written
-// behind the input position already consumed.
+// quarter of the lane's capacity, each copied into one of two page-locked bounce buffers of the
+// lane and handed to the same pipeline; its output comes back through two more.  The host
+// copies of sub-call k run while the GPU works on k-1, so the call costs max(host copies,
+// kernels) instead of their sum.  in == out is fine: output k-2 is written behind the input
+// position already consumed.
 static bool lane_ensure_bounce(Lane& L) {
   if (L.pin_cap >= L.cap_samples && L.pin_in[0]) return true;
   for (int b = 0; b < 2; b++) {
@@ -626,45 +629,118 @@ static bool lane_ensure_bounce(Lane& L) {
   return true;
 }
 
+// memcpy of a large piece split over a few threads: one host thread moves ~5 GB/s between
+// pageable and page-locked memory on the bench box, a 10-min channel is 115 MB each way, and the
+// kernels for it take 14 ms.  (The reference spends 4 OpenMP threads per handle by default.)
+static void copy_piece(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kMinSlice = 1u << 20;
+  constexpr int kThreads = 4;
+  int nt = (int)(bytes / kMinSlice);
+  if (nt > kThreads) nt = kThreads;
+  if (nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t slice = ((bytes / (size_t)nt) + 63) & ~(size_t)63;
+  std::thread th[kThreads - 1];
+  for (int t = 1; t < nt; t++) {
+    const size_t off = (size_t)t * slice;
+    const size_t len = off >= bytes ? 0 : (t == nt - 1 ? bytes - off : slice);
+    th[t - 1] = std::thread([=] {
+      if (len) memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len);
+    });
+  }
+  memcpy(dst, src, slice < bytes ? slice : bytes);
+  for (int t = 1; t < nt; t++) th[t - 1].join();
+}
+
 static bool enqueue_call_pageable(Handle* h, Lane& L, uint32_t n, const float* in, float* out,
                                   bool in_pageable, bool out_pageable) {
   if (!lane_ensure_bounce(L)) return false;
   const GeoK& gk = h->geo->k;
-  struct Pending { uint32_t pos = 0, m = 0; bool live = false; } pend[2];
-  uint32_t piece = (uint32_t)(sub_call_frames(gk) / 4 > 64 ? sub_call_frames(gk) / 4 : 64) * (uint32_t)gk.hop;
+  // pieces: a short first and last one (their copies are the only exposed ones), half a lane's
+  // capacity in between (full-size NLM chunks, few launch ramps)
+  const uint32_t ramp = (uint32_t)(sub_call_frames(gk) / 8 > 64 ? sub_call_frames(gk) / 8 : 64) * (uint32_t)gk.hop;
+  const uint32_t piece = (uint32_t)(sub_call_frames(gk) / 2 > 64 ? sub_call_frames(gk) / 2 : 64) * (uint32_t)gk.hop;
+  // The calling thread copies the input pieces in and enqueues; a helper thread of the call waits
+  // for each piece's D2H and copies it out, so input and output copies (each ~10 GB/s per thread)
+  // run side by side.  A bounce buffer pair b is handed back by the helper before the caller
+  // reuses it; the helper touches no engine state, only the lane's events and bounce buffers.
+  struct Piece { uint32_t pos, m; int b; };
+  struct Shared {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Piece> q;
+    bool busy[2] = {false, false};      // bounce pair b holds a piece that has not been copied out
+    bool done = false, failed = false;
+  } sh;
+  const int device = h->device;
+  std::thread helper([&] {
+    cudaSetDevice(device);
+    for (;;) {
+      Piece p;
+      {
+        std::unique_lock<std::mutex> lk(sh.mu);
+        sh.cv.wait(lk, [&] { return !sh.q.empty() || sh.done; });
+        if (sh.q.empty()) return;
+        p = sh.q.front();
+        sh.q.pop_front();
+      }
+      const bool ok = cudaEventSynchronize(L.ev_done[p.b]) == cudaSuccess;
+      if (ok && out_pageable) copy_piece(out + p.pos, L.pin_out[p.b], (size_t)p.m * sizeof(float));
+      {
+        std::lock_guard<std::mutex> lk(sh.mu);
+        sh.busy[p.b] = false;
+        if (!ok) sh.failed = true;
+      }
+      sh.cv.notify_all();
+    }
+  });
+  bool ok = true;
   uint32_t pos = 0;
-  auto drain = [&](int b) -> bool {
-    if (!pend[b].live) return true;
-    SB_CUDA(cudaEventSynchronize(L.ev_done[b]));
-    if (out_pageable) memcpy(out + pend[b].pos, L.pin_out[b], (size_t)pend[b].m * sizeof(float));
-    pend[b].live = false;
-    return true;
-  };
-  while (pos < n) {
+  while (pos < n && ok) {
     uint32_t m = n - pos;
     const uint32_t cap = max_sub_samples(h);
-    if (m > piece) m = piece;
+    if (pos == 0 && m > ramp) m = ramp;
+    else if (m > piece + ramp) m = piece;
+    else if (m > 2 * ramp) m -= ramp;
     if (m > cap) m = cap;
     const int b = (int)(L.io_seq & 1u);
-    // bounce buffer b: its previous H2D and D2H (sub-call k-2) must be over before it is reused
-    if (!drain(b)) return false;
-    if (L.io_seq >= 2) SB_CUDA(cudaEventSynchronize(L.ev_in[b]));
+    {
+      // bounce pair b: the piece it held (sub-call k-2) must have been copied out
+      std::unique_lock<std::mutex> lk(sh.mu);
+      sh.cv.wait(lk, [&] { return !sh.busy[b]; });
+      if (sh.failed) { ok = false; break; }
+    }
+    // ... and its H2D must be over before the input half is overwritten
+    if (L.io_seq >= 2 && cudaEventSynchronize(L.ev_in[b]) != cudaSuccess) { ok = false; break; }
     const float* src = in + pos;
     if (in_pageable) {
-      memcpy(L.pin_in[b], in + pos, (size_t)m * sizeof(float));
+      copy_piece(L.pin_in[b], in + pos, (size_t)m * sizeof(float));
       src = L.pin_in[b];
     }
     float* dst = out_pageable ? L.pin_out[b] : out + pos;
     int used = 0;
-    if (!enqueue_host_sub(h, L, m, src, dst, &used)) return false;
-    pend[used].pos = pos;
-    pend[used].m = m;
-    pend[used].live = true;
+    if (!enqueue_host_sub(h, L, m, src, dst, &used)) { ok = false; break; }
+    {
+      std::lock_guard<std::mutex> lk(sh.mu);
+      sh.busy[used] = true;
+      sh.q.push_back(Piece{pos, m, used});
+    }
+    sh.cv.notify_all();
     pos += m;
   }
-  const int first = (int)(L.io_seq & 1u);       // the older of the two pending sub-calls
-  if (!drain(first) || !drain(first ^ 1)) return false;
-  return true;
+  {
+    std::lock_guard<std::mutex> lk(sh.mu);
+    sh.done = true;
+  }
+  sh.cv.notify_all();
+  helper.join();
+  if (sh.failed) {
+    set_error("pageable output copy", cudaGetLastError(), __FILE__, __LINE__);
+    ok = false;
+  }
+  return ok;
 }
 
 // Enqueues the whole call on the lane; does not synchronise (device / page-locked buffers).
