@@ -45,3 +45,34 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     r = run_bench("--steps", "1", "--warmup", "0", "--no-cpu-baseline")
     assert r.returncode != 0                           # no CPU fallback: it must fail loudly
     assert "CUDA" in (r.stderr + r.stdout) or "device" in (r.stderr + r.stdout)
+
+
+def test_workloads_follow_the_baseline_configs():
+    """bench.py --config N: geometry, stream counts and audio accounting of BASELINE configs 2-5;
+    config 3 shards its 4096 streams over the ranks without gaps or overlaps (no data-path
+    collective: every rank owns a contiguous block)."""
+    import sys
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from libspecbleach_b200.sharding import shard_bounds
+    w2 = bench.Workload(2, 8, 3)
+    assert (w2.sr, w2.frame, w2.fft, w2.hop, w2.bins) == (48000, 2400, 3200, 600, 1601)
+    assert w2.n_streams == 2 and w2.job_audio_seconds() == 8 * 600.0 and w2.scaling == "weak"
+    for world in (1, 2, 4, 8, 3):
+        owned = []
+        for rank in range(world):
+            w = bench.Workload(3, world, rank)
+            lo, hi = shard_bounds(4096, world, rank)
+            assert w.n_streams == hi - lo and w.wave == 128
+            owned += list(range(lo, hi))
+            assert w.job_audio_seconds() == 4096 * 60.0 and w.scaling == "strong"
+        assert owned == list(range(4096))
+    w4 = bench.Workload(4, 1, 0)
+    assert (w4.sr, w4.frame, w4.fft, w4.hop, w4.bins) == (44100, 2205, 3006, 551, 1504)
+    assert w4.n_learn == 0 and [p["noise_estimation_method"] for p in w4.params] == [0, 2]
+    assert w4.n // w4.hop == 288130 or w4.n // w4.hop == 288131
+    w5 = bench.Workload(5, 1, 0)
+    assert (w5.frame, w5.fft, w5.hop, w5.bins) == (7392, 8192, 1848, 4097) and w5.n_streams == 8
+    assert w5.job_audio_seconds() == 120.0
+    # both arms describe the workload identically (the driver compares their `config`)
+    assert bench.Workload(3, 4, 0).config_dict() == bench.Workload(3, 4, 2).config_dict()
