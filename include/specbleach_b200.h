@@ -172,6 +172,15 @@ bool specbleach_b200_get_geometry(SpectralBleachHandle instance, uint32_t* frame
  * the FP32 pipe and not by HBM (MEASURED_PEAKS.json has no FP32 figure). */
 double specbleach_b200_debug_fp32_peak_tflops(void);
 
+/* With SB_GUARD=1 in the environment when the library is loaded, every device allocation
+ * carries a 4 KB zone of 0xFF bytes on each side (an out-of-bounds float load reads a NaN, an
+ * out-of-bounds store damages the zone).  Returns the number of allocations, live or freed since
+ * the previous call, whose zones were written; -1 when guarding is off.  Synchronises all
+ * devices.  SB_GUARD=selftest additionally stores one byte behind the first live allocation
+ * before checking, so the call must then return >= 1 (tests/test_gpu_guard.py).
+ * (compute-sanitizer's memcheck is the better tool where it can be run.) */
+int specbleach_b200_debug_check_guards(void);
+
 /* Single-kernel entry points used by the parity tests (host buffers). ------ */
 /* NLM over a whole SNR map snr[frames][bins] (row-major, pitch = bins):
  * out[j] = filtered frame j-4 as the reference returns it after pushing frame

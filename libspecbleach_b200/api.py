@@ -64,7 +64,7 @@ EXTENSION_SYMBOLS = ["specbleach_b200_" + n for n in (
     "device_count", "set_device", "last_error", "host_alloc", "host_free", "configure",
     "process_device", "process_batch", "process_batch_device", "profile", "stats_reset",
     "stats_get", "stats_classes", "stats_class_name", "stats_class", "get_geometry",
-    "debug_fp32_peak_tflops", "debug_nlm", "debug_rfft", "profile_save", "profile_load",
+    "debug_fp32_peak_tflops", "debug_check_guards", "debug_nlm", "debug_rfft", "profile_save", "profile_load",
     "state_size", "state_save", "state_load", "process_interleaved", "process_tiled", "process_tiled_batch", "set_strategy")]
 
 
@@ -155,6 +155,7 @@ def lib():
     L.specbleach_b200_get_geometry.restype = C.c_bool
     L.specbleach_b200_get_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
     L.specbleach_b200_debug_fp32_peak_tflops.restype = C.c_double
+    L.specbleach_b200_debug_check_guards.restype = C.c_int
     L.specbleach_b200_debug_nlm.restype = C.c_bool
     L.specbleach_b200_debug_nlm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float,
                                             C.c_void_p]

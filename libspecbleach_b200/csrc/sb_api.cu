@@ -327,10 +327,15 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 
 extern "C" {
 
+int specbleach_b200_debug_check_guards(void) {
+  std::lock_guard<std::recursive_mutex> engine_lock(sb::engine_mutex());
+  return sb::check_guards();
+}
+
 double specbleach_b200_debug_fp32_peak_tflops(void) {
   float* d = nullptr;
   const int blocks = 148 * 8, threads = 256, iters = 4096;
-  if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return 0.0;
+  if (sb::dev_malloc(&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return 0.0;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -348,7 +353,7 @@ double specbleach_b200_debug_fp32_peak_tflops(void) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFree(d);
+  sb::dev_free(d);
   return best;
 }
 
@@ -365,8 +370,8 @@ bool specbleach_b200_debug_nlm(const float* snr, uint32_t frames, uint32_t bins,
   const size_t rows = sb::kSnrHist + frames;
   float *dS = nullptr, *dO = nullptr;
   bool ok = true;
-  if (cudaMalloc(&dS, rows * Kp * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&dO, (size_t)frames * Kp * sizeof(float)) != cudaSuccess) {
+  if (sb::dev_malloc(&dS, rows * Kp * sizeof(float)) != cudaSuccess ||
+      sb::dev_malloc(&dO, (size_t)frames * Kp * sizeof(float)) != cudaSuccess) {
     sb::set_error("cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
     ok = false;
   }
@@ -393,8 +398,8 @@ bool specbleach_b200_debug_nlm(const float* snr, uint32_t frames, uint32_t bins,
   }
   if (!ok && cudaPeekAtLastError() != cudaSuccess)
     sb::set_error("debug_nlm", cudaGetLastError(), __FILE__, __LINE__);
-  cudaFree(dS);
-  cudaFree(dO);
+  sb::dev_free(dS);
+  sb::dev_free(dO);
   return ok;
 }
 
@@ -406,11 +411,11 @@ bool specbleach_b200_debug_rfft(uint32_t fft_size, uint32_t frames, const float*
   const sb::GeoK& g = G->k;
   const size_t Kp = g.Kp, N = g.N;
   float *dx = nullptr, *dre = nullptr, *dim = nullptr, *dp = nullptr, *dsyn = nullptr;
-  bool ok = cudaMalloc(&dx, frames * N * sizeof(float)) == cudaSuccess &&
-            cudaMalloc(&dre, frames * Kp * sizeof(float)) == cudaSuccess &&
-            cudaMalloc(&dim, frames * Kp * sizeof(float)) == cudaSuccess &&
-            cudaMalloc(&dp, frames * Kp * sizeof(float)) == cudaSuccess &&
-            cudaMalloc(&dsyn, frames * (size_t)g.frame_p * sizeof(float)) == cudaSuccess;
+  bool ok = sb::dev_malloc(&dx, frames * N * sizeof(float)) == cudaSuccess &&
+            sb::dev_malloc(&dre, frames * Kp * sizeof(float)) == cudaSuccess &&
+            sb::dev_malloc(&dim, frames * Kp * sizeof(float)) == cudaSuccess &&
+            sb::dev_malloc(&dp, frames * Kp * sizeof(float)) == cudaSuccess &&
+            sb::dev_malloc(&dsyn, frames * (size_t)g.frame_p * sizeof(float)) == cudaSuccess;
   if (ok) ok = cudaMemcpy(dx, in, frames * N * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
   // hop == N: frame f = dx[f*N, (f+1)*N)
   ok = ok && sb::launch_forward(g, dx, (int)frames, dre, dim, dp, 0);
@@ -432,7 +437,7 @@ bool specbleach_b200_debug_rfft(uint32_t fft_size, uint32_t frames, const float*
   }
   if (!ok && cudaPeekAtLastError() != cudaSuccess)
     sb::set_error("debug_rfft", cudaGetLastError(), __FILE__, __LINE__);
-  cudaFree(dx); cudaFree(dre); cudaFree(dim); cudaFree(dp); cudaFree(dsyn);
+  sb::dev_free(dx); sb::dev_free(dre); sb::dev_free(dim); sb::dev_free(dp); sb::dev_free(dsyn);
   sb::free_geometry(G);
   return ok;
 }

@@ -242,6 +242,17 @@ struct Handle {
 void set_error(const char* what, cudaError_t e, const char* file, int line);
 const char* last_error();
 extern uint64_t g_launches;     // kernels launched by this library
+
+// Every device allocation of the library goes through these two.  With SB_GUARD=1 in the
+// environment each allocation gets a 4 KB zone of 0xFF bytes (float NaNs) on both sides:
+// an out-of-bounds store damages a zone (check_guards / specbleach_b200_debug_check_guards
+// counts them), an out-of-bounds float load drags a NaN into the output.  compute-sanitizer
+// is not available on the GPU boxes of this project; this is the stand-in.
+cudaError_t dev_malloc(void** p, size_t bytes);
+void dev_free(void* p);
+int check_guards();             // allocations (live, or freed since the last call) with a damaged zone; -1 on error
+template <typename T>
+static inline cudaError_t dev_malloc(T** p, size_t bytes) { return dev_malloc((void**)p, bytes); }
 extern bool g_profile;          // record NLM events
 
 #define SB_CUDA(expr)                                              \

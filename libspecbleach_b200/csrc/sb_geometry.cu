@@ -18,9 +18,9 @@ static std::map<std::tuple<int, uint32_t, uint32_t>, Geometry*> g_geo_cache;
 template <typename T>
 static T* upload(Geometry* G, const std::vector<T>& v) {
   T* d = nullptr;
-  if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  if (dev_malloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
   if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaFree(d);
+    dev_free(d);
     return nullptr;
   }
   G->dev_allocs.push_back(d);
@@ -310,7 +310,7 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
   if (!g.win || !g.tw || !g.twn || !g.twg || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
       !g.veto_t || !g.band_of_bin) {
     set_error("geometry upload", cudaGetLastError(), __FILE__, __LINE__);
-    for (void* p : G->dev_allocs) cudaFree(p);
+    for (void* p : G->dev_allocs) dev_free(p);
     delete G;
     return nullptr;
   }
@@ -363,7 +363,7 @@ Geometry* make_fft_geometry(int fft_size) {
 
 void free_geometry(Geometry* G) {
   if (!G) return;
-  for (void* p : G->dev_allocs) cudaFree(p);
+  for (void* p : G->dev_allocs) dev_free(p);
   delete G;
 }
 

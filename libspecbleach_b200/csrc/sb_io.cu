@@ -303,8 +303,8 @@ bool state_load(Handle* h, const void* blob, size_t bytes) {
   if (new_method != h->est_method || (want_est != 0) != (h->d_est != nullptr) ||
       (size_t)want_est != h->est_floats) {
     float* fresh = nullptr;
-    if (want_est) SB_CUDA(cudaMalloc(&fresh, (size_t)want_est * sizeof(float)));
-    if (h->d_est) cudaFree(h->d_est);
+    if (want_est) SB_CUDA(dev_malloc(&fresh, (size_t)want_est * sizeof(float)));
+    if (h->d_est) dev_free(h->d_est);
     h->d_est = fresh;
     h->est_floats = (size_t)want_est;
     h->est_method = new_method;
@@ -421,8 +421,8 @@ bool process_interleaved(Handle** hs, uint32_t channels, uint32_t frames, int fo
   unsigned char* d_pcm = nullptr;
   float* d_planar = nullptr;
   bool ok = true;
-  if (cudaMalloc(&d_pcm, bytes) != cudaSuccess ||
-      cudaMalloc(&d_planar, pitch * channels * sizeof(float)) != cudaSuccess) {
+  if (dev_malloc(&d_pcm, bytes) != cudaSuccess ||
+      dev_malloc(&d_planar, pitch * channels * sizeof(float)) != cudaSuccess) {
     set_error("cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
     ok = false;
   }
@@ -449,8 +449,8 @@ bool process_interleaved(Handle** hs, uint32_t channels, uint32_t frames, int fo
     if (!ok && cudaPeekAtLastError() != cudaSuccess)
       set_error("process_interleaved", cudaGetLastError(), __FILE__, __LINE__);
   }
-  cudaFree(d_pcm);
-  cudaFree(d_planar);
+  dev_free(d_pcm);
+  dev_free(d_planar);
   return ok;
 }
 

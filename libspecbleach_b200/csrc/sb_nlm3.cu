@@ -494,11 +494,11 @@ bool launch_nlm3(const GeoK& g, const float* S, int first_target_row, int target
     const size_t need = (size_t)(targets < chunk ? targets : chunk) * (size_t)nfull;
     if (ref.pairs < need) {
       SB_CUDA(cudaStreamSynchronize(st));
-      if (ref.W) cudaFree(ref.W);
-      if (ref.F) cudaFree(ref.F);
+      if (ref.W) dev_free(ref.W);
+      if (ref.F) dev_free(ref.F);
       ref = Scratch3();
-      SB_CUDA(cudaMalloc(&ref.W, need * WPITCH3 * sizeof(float)));
-      SB_CUDA(cudaMalloc(&ref.F, need * FW3 * sizeof(unsigned)));
+      SB_CUDA(dev_malloc(&ref.W, need * WPITCH3 * sizeof(float)));
+      SB_CUDA(dev_malloc(&ref.F, need * FW3 * sizeof(unsigned)));
       ref.pairs = need;
     }
     sc = ref;

@@ -27,3 +27,14 @@ def gpu():
         pytest.fail("GPU test selected but no CUDA device is visible (no CPU fallback exists)")
     sb.set_device(0)
     return sb
+
+
+@pytest.fixture(scope="session", autouse=True)
+def guard_zones_intact_at_exit():
+    """`SB_GUARD=1 python -m pytest tests -m gpu` runs the whole GPU suite with guard zones
+    around every device allocation (include/specbleach_b200.h); none may be written."""
+    yield
+    import os
+    if os.environ.get("SB_GUARD", "0") not in ("", "0", "selftest"):
+        from libspecbleach_b200 import api
+        assert api.lib().specbleach_b200_debug_check_guards() == 0
