@@ -546,14 +546,24 @@ __global__ void onset_scan_kernel(int nb, int rows, float* __restrict__ band_e, 
 // ---------------------------------------------------------------------------
 // (frame, band): band energies, spreading, tonality -> a_t[b]
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float spreading_gain(float dz, float level_db) {
-  // masking_estimator.c:305-318
+__device__ __forceinline__ float spreading_exponent(float dz, float level_db) {
+  // masking_estimator.c:305-318: the spreading gain is 10^(this)
   const float s_up = fminf(fmaxf(15.0f - ((level_db - 40.0f) * 0.2f), 5.0f), 15.0f);
   const float s_total = (25.0f + s_up) / 2.0f;
   const float s_offset = (25.0f - s_up) / 2.0f;
   const float y = dz + 0.474f;
   const float sf_db = 15.81f + (s_offset * y) - (s_total * sqrtf(1.0f + (y * y)));
-  return exp10f(sf_db / 10.0f);
+  return sf_db / 10.0f;
+}
+
+// (E * 10^t)^0.4 as 2^(0.4 (log2 E + t log2 10)): the exponent in double (exact to float
+// precision, log2 E computed once per band), one exp2f on the fraction.  Within 2 ulp of the exact
+// value, where powf(E * exp10f(t), 0.4f) stacks three roundings; 625 x 2 of these per frame.
+__device__ __forceinline__ float spread_term(double lg2_energy, float t) {
+  const double a = (double)kAdditivityExp * fma((double)t, 3.321928094887362, lg2_energy);
+  if (!(a > -125.0)) return 0.0f;          // E == 0 (log2 = -inf) and products below float range
+  const double r = rint(a);
+  return exp2f((float)(a - r)) * __int_as_float(((int)r + 127) << 23);
 }
 
 __global__ void __launch_bounds__(256)
@@ -564,6 +574,7 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
   __shared__ float LV[2][kBandPitch], SPR[2][kBandPitch];
   __shared__ float PART[6][kMaxBandTasks];
   __shared__ float TERM[2][kMaxBands][kMaxBands + 1];
+  __shared__ double LG2E[2][kBandPitch];
   const int i = first_active + blockIdx.x;
   const size_t ro = (size_t)i * g.Kp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -646,7 +657,10 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
   const int nspec = two_d ? 2 : 1;
   if (threadIdx.x < nspec * kBandPitch) {
     const int s = threadIdx.x / kBandPitch, b = threadIdx.x % kBandPitch;
-    if (b < g.nb) LV[s][b] = (10.0f * log10f(E[s][b] + kSpectralEps)) + kDbFsToSpl;
+    if (b < g.nb) {
+      LV[s][b] = (10.0f * log10f(E[s][b] + kSpectralEps)) + kDbFsToSpl;
+      LG2E[s][b] = log2((double)E[s][b]);
+    }
   }
   __syncthreads();
   // spreading terms (E_j g(i-j, L_j))^0.4 for every (spectrum, band i, band j): all threads
@@ -657,8 +671,7 @@ band_kernel(const GeoK g, int first_active, int two_d, const float* __restrict__
     const int r = item - s * nb2;
     const int b = (int)(((unsigned)r * nbmagic) >> 16), j = r - b * g.nb;
     const float dz = (float)b - (float)j;
-    const float gain = spreading_gain(dz, LV[s][j]);
-    TERM[s][b][j] = powf(E[s][j] * gain, kAdditivityExp);
+    TERM[s][b][j] = spread_term(LG2E[s][j], spreading_exponent(dz, LV[s][j]));
   }
   __syncthreads();
   if (threadIdx.x < nspec * kBandPitch) {
