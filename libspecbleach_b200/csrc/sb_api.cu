@@ -36,7 +36,7 @@ bool profile_available(SpectralBleachHandle inst, int mode) {
 bool load_profile(SpectralBleachHandle inst, const float* prof, uint32_t size, uint32_t blocks,
                   int mode) {
   if (!inst || !prof || !valid_mode(mode)) return false;
-  return sb::handle_load_profile(H(inst), prof, size, blocks, mode);
+  return sb::guarded(false, [&] { return sb::handle_load_profile(H(inst), prof, size, blocks, mode); });
 }
 
 }  // namespace
@@ -46,7 +46,7 @@ extern "C" {
 // ------------------------------- 1D ---------------------------------------
 SpectralBleachHandle specbleach_initialize(uint32_t sample_rate, float frame_size) {
   if (sample_rate < 4000 || sample_rate > 192000 || !(frame_size > 0.0f)) return nullptr;
-  return sb::handle_create(false, sample_rate, frame_size);
+  return sb::guarded((Handle*)nullptr, [&] { return sb::handle_create(false, sample_rate, frame_size); });
 }
 void specbleach_free(SpectralBleachHandle instance) { sb::handle_destroy(H(instance)); }
 
@@ -65,12 +65,12 @@ bool specbleach_load_parameters(SpectralBleachHandle instance,
   p.strength = q.suppression_strength / 100.f;
   p.aggressiveness = q.aggressiveness;
   p.tonal = db_to_coefficient(q.tonal_reduction * -1.f);
-  return sb::handle_load_parameters(H(instance), p);
+  return sb::guarded(false, [&] { return sb::handle_load_parameters(H(instance), p); });
 }
 bool specbleach_process(SpectralBleachHandle instance, uint32_t n, const float* input,
                         float* output) {
   if (!instance || n == 0 || !input || !output) return false;
-  return sb::process_call(H(instance), n, input, output, false);
+  return sb::guarded(false, [&] { return sb::process_call(H(instance), n, input, output, false); });
 }
 uint32_t specbleach_get_latency(SpectralBleachHandle instance) {
   if (!instance) return 0;
@@ -103,7 +103,7 @@ bool specbleach_noise_profile_available_for_mode(SpectralBleachHandle instance, 
 // ------------------------------- 2D ---------------------------------------
 SpectralBleachHandle specbleach_2d_initialize(uint32_t sample_rate, float frame_size) {
   if (sample_rate == 0 || !(frame_size > 0.0f)) return nullptr;
-  return sb::handle_create(true, sample_rate, frame_size);
+  return sb::guarded((Handle*)nullptr, [&] { return sb::handle_create(true, sample_rate, frame_size); });
 }
 void specbleach_2d_free(SpectralBleachHandle instance) { sb::handle_destroy(H(instance)); }
 
@@ -122,12 +122,12 @@ bool specbleach_2d_load_parameters(SpectralBleachHandle instance,
   p.strength = q.suppression_strength / 100.f;
   p.aggressiveness = q.aggressiveness;
   p.tonal = db_to_coefficient(q.tonal_reduction * -1.f);
-  return sb::handle_load_parameters(H(instance), p);
+  return sb::guarded(false, [&] { return sb::handle_load_parameters(H(instance), p); });
 }
 bool specbleach_2d_process(SpectralBleachHandle instance, uint32_t n, const float* input,
                            float* output) {
   if (!instance || n == 0 || !input || !output) return false;
-  return sb::process_call(H(instance), n, input, output, false);
+  return sb::guarded(false, [&] { return sb::process_call(H(instance), n, input, output, false); });
 }
 uint32_t specbleach_2d_get_latency(SpectralBleachHandle instance) {
   if (!instance) return 0;
@@ -210,29 +210,32 @@ bool specbleach_b200_configure(uint32_t chunk_frames, uint32_t lanes) {
 bool specbleach_b200_process_device(SpectralBleachHandle instance, uint32_t n,
                                     const float* d_input, float* d_output) {
   if (!instance || n == 0 || !d_input || !d_output) return false;
-  return sb::process_call(H(instance), n, d_input, d_output, true);
+  return sb::guarded(false, [&] { return sb::process_call(H(instance), n, d_input, d_output, true); });
 }
 bool specbleach_b200_process_batch(SpectralBleachHandle* instances, uint32_t count,
                                    const uint32_t* n, const float* const* inputs,
                                    float* const* outputs) {
   if (!instances || !n || !inputs || !outputs) return false;
-  return sb::process_batch(reinterpret_cast<Handle**>(instances), count, n, inputs, outputs,
-                           false);
+  return sb::guarded(false, [&] {
+    return sb::process_batch(reinterpret_cast<Handle**>(instances), count, n, inputs, outputs, false);
+  });
 }
 bool specbleach_b200_process_batch_device(SpectralBleachHandle* instances, uint32_t count,
                                           const uint32_t* n, const float* const* d_inputs,
                                           float* const* d_outputs) {
   if (!instances || !n || !d_inputs || !d_outputs) return false;
-  return sb::process_batch(reinterpret_cast<Handle**>(instances), count, n, d_inputs, d_outputs,
-                           true);
+  return sb::guarded(false, [&] {
+    return sb::process_batch(reinterpret_cast<Handle**>(instances), count, n, d_inputs, d_outputs, true);
+  });
 }
 
 bool specbleach_b200_process_tiled(SpectralBleachHandle instance, uint32_t n, const float* input,
                                    float* output, uint32_t tiles, uint32_t warmup_frames,
                                    const int* devices, uint32_t device_count, uint32_t flags) {
   if (!instance || n == 0 || !input || !output) return false;
-  return sb::process_tiled(H(instance), n, input, output, tiles, warmup_frames, devices, device_count,
-                           flags);
+  return sb::guarded(false, [&] {
+    return sb::process_tiled(H(instance), n, input, output, tiles, warmup_frames, devices, device_count, flags);
+  });
 }
 
 bool specbleach_b200_process_tiled_batch(SpectralBleachHandle* instances, uint32_t count,
@@ -240,8 +243,10 @@ bool specbleach_b200_process_tiled_batch(SpectralBleachHandle* instances, uint32
                                          float* const* outputs, uint32_t tiles, uint32_t warmup_frames,
                                          const int* devices, uint32_t device_count, uint32_t flags) {
   if (!instances || !number_of_samples || !inputs || !outputs || count == 0) return false;
-  return sb::process_tiled_batch(reinterpret_cast<Handle**>(instances), count, number_of_samples, inputs,
-                                 outputs, tiles, warmup_frames, devices, device_count, flags);
+  return sb::guarded(false, [&] {
+    return sb::process_tiled_batch(reinterpret_cast<Handle**>(instances), count, number_of_samples, inputs,
+                                   outputs, tiles, warmup_frames, devices, device_count, flags);
+  });
 }
 
 bool specbleach_b200_set_strategy(SpectralBleachHandle instance, int gain_type, int suppression_type,

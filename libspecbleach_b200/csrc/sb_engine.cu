@@ -17,6 +17,7 @@
 #include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <system_error>
 #include <thread>
 
 namespace sb {
@@ -739,12 +740,18 @@ static void copy_piece(void* dst, const void* src, size_t bytes) {
   for (int t = 1; t < nt; t++) {
     const size_t off = (size_t)t * slice;
     const size_t len = off >= bytes ? 0 : (t == nt - 1 ? bytes - off : slice);
-    th[t - 1] = std::thread([=] {
+    auto work = [=] {
       if (len) memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len);
-    });
+    };
+    try {
+      th[t - 1] = std::thread(work);
+    } catch (const std::system_error&) {   // no thread to be had: this slice on the calling thread
+      work();
+    }
   }
   memcpy(dst, src, slice < bytes ? slice : bytes);
-  for (int t = 1; t < nt; t++) th[t - 1].join();
+  for (int t = 1; t < nt; t++)
+    if (th[t - 1].joinable()) th[t - 1].join();
 }
 
 static bool enqueue_call_pageable(Handle* h, Lane& L, uint32_t n, const float* in, float* out,
@@ -768,7 +775,7 @@ static bool enqueue_call_pageable(Handle* h, Lane& L, uint32_t n, const float* i
     bool done = false, failed = false;
   } sh;
   const int device = h->device;
-  std::thread helper([&] {
+  auto drain = [&] {
     cudaSetDevice(device);
     for (;;) {
       Piece p;
@@ -788,7 +795,14 @@ static bool enqueue_call_pageable(Handle* h, Lane& L, uint32_t n, const float* i
       }
       sh.cv.notify_all();
     }
-  });
+  };
+  std::thread helper;
+  try {
+    helper = std::thread(drain);
+  } catch (const std::system_error&) {
+    set_error_msg("specbleach-b200: cannot start the copy-out thread of a pageable call");
+    return false;
+  }
   bool ok = true;
   uint32_t pos = 0;
   while (pos < n && ok) {
@@ -1139,7 +1153,12 @@ bool process_tiled_batch(Handle** hs, uint32_t count, const uint32_t* ns, const 
       Tile& t = J.plan[i];
       // tile 0 continues the handle on its own device; the others go round the listed devices
       if (i > 0 && devices && device_count) t.device = devices[i % device_count];
-      if (cudaSetDevice(t.device) != cudaSuccess) { ok = false; break; }
+      if (cudaSetDevice(t.device) != cudaSuccess) {
+        set_error("specbleach_b200_process_tiled: cudaSetDevice on a listed device", cudaGetLastError(),
+                  __FILE__, __LINE__);
+        ok = false;
+        break;
+      }
       t.lane = get_lane((int)(next_lane[t.device]++ % (size_t)nlanes), J.h->geo->k);
       if (!t.lane) { ok = false; break; }
       if (i == 0) {

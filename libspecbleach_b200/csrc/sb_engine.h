@@ -3,6 +3,7 @@
 
 #include "sb_common.h"
 
+#include <exception>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -56,6 +57,23 @@ bool stats_collect(Context& c);
 size_t state_size(Handle* h);
 bool state_save(Handle* h, void* blob, size_t bytes);
 bool state_load(Handle* h, const void* blob, size_t bytes);
+
+void set_error_msg(const char* msg);
+
+// No C++ exception may cross the C boundary (std::bad_alloc from a host-side vector, a
+// std::system_error from a mutex): the call fails the way the reference's do -- NULL / false --
+// and specbleach_b200_last_error() says why.
+template <typename R, typename F>
+R guarded(R on_error, F&& f) noexcept {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    set_error_msg(e.what());
+  } catch (...) {
+    set_error_msg("specbleach-b200: unknown C++ exception");
+  }
+  return on_error;
+}
 
 // sb_geometry.cu: private geometry for the FFT-only debug entry point
 Geometry* make_fft_geometry(int fft_size);

@@ -463,30 +463,42 @@ extern "C" {
 
 bool specbleach_b200_profile_save(void* instance, const char* path) {
   if (!instance || !path) return false;
-  std::vector<unsigned char> buf;
-  if (!sb::profile_serialize(static_cast<sb::Handle*>(instance), buf)) return false;
-  FILE* f = fopen(path, "wb");
-  if (!f) {
-    sb::set_error_msg("specbleach-b200: cannot open noise profile file for writing");
-    return false;
-  }
-  const bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-  return (fclose(f) == 0) && ok;
+  return sb::guarded(false, [&] {
+    std::vector<unsigned char> buf;
+    if (!sb::profile_serialize(static_cast<sb::Handle*>(instance), buf)) return false;
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+      sb::set_error_msg("specbleach-b200: cannot open noise profile file for writing");
+      return false;
+    }
+    const bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    return (fclose(f) == 0) && ok;
+  });
 }
 
 bool specbleach_b200_profile_load(void* instance, const char* path) {
   if (!instance || !path) return false;
-  FILE* f = fopen(path, "rb");
-  if (!f) {
-    sb::set_error_msg("specbleach-b200: cannot open noise profile file");
-    return false;
-  }
-  std::vector<unsigned char> buf;
-  unsigned char tmp[65536];
-  size_t n;
-  while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
-  fclose(f);
-  return sb::profile_deserialize(static_cast<sb::Handle*>(instance), buf.data(), buf.size());
+  return sb::guarded(false, [&] {
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+      sb::set_error_msg("specbleach-b200: cannot open noise profile file");
+      return false;
+    }
+    // a profile file is a header plus four rows of at most fft_size floats: anything beyond a few
+    // MB is not one, and is not read into memory
+    constexpr size_t kMaxProfileFile = 64u << 20;
+    std::vector<unsigned char> buf;
+    unsigned char tmp[65536];
+    size_t n;
+    while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0 && buf.size() <= kMaxProfileFile)
+      buf.insert(buf.end(), tmp, tmp + n);
+    fclose(f);
+    if (buf.size() > kMaxProfileFile) {
+      sb::set_error_msg("specbleach-b200: noise profile file too large");
+      return false;
+    }
+    return sb::profile_deserialize(static_cast<sb::Handle*>(instance), buf.data(), buf.size());
+  });
 }
 
 size_t specbleach_b200_state_size(void* instance) {
@@ -494,17 +506,19 @@ size_t specbleach_b200_state_size(void* instance) {
 }
 bool specbleach_b200_state_save(void* instance, void* blob, size_t bytes) {
   if (!instance || !blob) return false;
-  return sb::state_save(static_cast<sb::Handle*>(instance), blob, bytes);
+  return sb::guarded(false, [&] { return sb::state_save(static_cast<sb::Handle*>(instance), blob, bytes); });
 }
 bool specbleach_b200_state_load(void* instance, const void* blob, size_t bytes) {
   if (!instance || !blob) return false;
-  return sb::state_load(static_cast<sb::Handle*>(instance), blob, bytes);
+  return sb::guarded(false, [&] { return sb::state_load(static_cast<sb::Handle*>(instance), blob, bytes); });
 }
 
 bool specbleach_b200_process_interleaved(void** instances, uint32_t channels, uint32_t frames,
                                          int format, const void* input, void* output) {
-  return sb::process_interleaved(reinterpret_cast<sb::Handle**>(instances), channels, frames,
-                                 format, input, output);
+  return sb::guarded(false, [&] {
+    return sb::process_interleaved(reinterpret_cast<sb::Handle**>(instances), channels, frames, format, input,
+                                   output);
+  });
 }
 
 }  // extern "C"
