@@ -77,6 +77,14 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   int pass_l[14], pass_s[14], pass_tstep[14], pass_nbf[14];
   unsigned pass_smagic[14], pass_nbfmagic[14];
   int fft_threads;            // CTA size of the FFT kernels (fill_passes: fewest idle warp rounds)
+  // Length the Stockham passes above work on: M, or -- when M has a prime factor >= 32 (N = 3006 =
+  // 2 3^2 167 at 44.1 kHz / 50 ms) -- the power of two L >= 2M - 1 of Bluestein's chirp-z form,
+  // in which the M-point DFT is a cyclic convolution of length L: two L-point FFTs and three
+  // pointwise products instead of an O(r) sum per output of the radix-r pass.
+  int fft_len;                // M or L
+  int bl_L;                   // 0: plain mixed radix
+  const float2* bl_w;         // [M] chirp exp(-i pi n^2 / M)
+  const float2* bl_B;         // [L] FFT_L of the wrapped conjugate chirp, divided by L
   int nb;                                // number of Bark bands (<= 25)
   int band_start[kMaxBands + 1];         // band b = [band_start[b], band_start[b+1])
   // Bark bands differ wildly in width (3 bins ... two thirds of the spectrum): per-frame band
@@ -92,7 +100,7 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   float spl_ref;                         // absolute_hearing_thresholds.c:118-139
   float scale;                           // stft_windows.c:103-118
   const float* win;                      // [frame] periodic Hann
-  const float2* tw;                      // [M]   exp(-2 pi i k / M)
+  const float2* tw;                      // [fft_len] exp(-2 pi i k / fft_len)
   const float2* twn;                     // [M+1] exp(-2 pi i k / N)
   const double2* twg;                    // per generic-radix pass: r roots of unity in double
   int twg_off[14];                       // offset of pass f inside twg (-1: radix 2/4 pass)

@@ -34,13 +34,14 @@ static const float kBark[25] = {100.f,  200.f,  300.f,  400.f,  510.f,  630.f,  
                                 9500.f, 12000.f, 15500.f, 19000.f};
 
 static void fill_passes(GeoK& g) {
-  int len = g.M, s = 1;
+  const int FL = g.fft_len;
+  int len = FL, s = 1;
   for (int f = 0; f < g.nfac; f++) {
     const int r = g.fac[f];
     g.pass_l[f] = len / r;
     g.pass_s[f] = s;
-    g.pass_tstep[f] = g.M / len;
-    g.pass_nbf[f] = g.M / r;
+    g.pass_tstep[f] = FL / len;
+    g.pass_nbf[f] = FL / r;
     g.pass_smagic[f] = (unsigned)((0x100000000ull + (unsigned long long)s - 1) / (unsigned long long)s);
     g.pass_nbfmagic[f] = (unsigned)((0x100000000ull + (unsigned long long)g.pass_nbf[f] - 1) /
                                     (unsigned long long)g.pass_nbf[f]);
@@ -66,7 +67,8 @@ static void fill_passes(GeoK& g) {
     }
     cost += 2.0 * (double)((g.M + T - 1) / T) * warps * 2.0;      // load and split / crop loops
     cost += 0.25 * g.nfac * warps;                                 // barrier per pass
-    const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
+    if (g.bl_L) cost *= 2.0;                                       // both transforms of the convolution
+    const size_t smem = 2 * sizeof(float2) * (size_t)FL;
     int ctas = (int)((227 * 1024) / (smem + 1024));
     const int by_regs = 65536 / (56 * warps * 32);
     if (by_regs < ctas) ctas = by_regs;
@@ -76,6 +78,9 @@ static void fill_passes(GeoK& g) {
     if (resident < 24) cost *= 24.0 / resident;
     if (cost < best - 1e-9) { best = cost; g.fft_threads = T; }
   }
+  // Bluestein lengths are 2^a, 3 2^a or 5 2^a: 256 threads divide every pass's butterfly count
+  // (measured at L = 3072: 192 -> 0.278 ms per 4800 frames, 256 -> 0.255, 384 -> 0.255, 512 -> 0.274)
+  if (g.bl_L >= 2048) g.fft_threads = 256;
   // measurement knob: SB_FFT_THREADS=<32..512> overrides the choice
   if (const char* e = getenv("SB_FFT_THREADS")) {
     const int t = atoi(e);
@@ -111,6 +116,79 @@ static std::vector<double2> generic_roots(GeoK& g) {
   }
   if (t.empty()) t.push_back(make_double2(1.0, 0.0));
   return t;
+}
+
+static int largest_prime_factor(int m) {
+  int best = 1;
+  for (int p = 2; p * p <= m; p++)
+    while (m % p == 0) { best = p; m /= p; }
+  return m > 1 ? m : best;
+}
+
+// Smallest length >= need of the form 2^a, 3 2^a or 5 2^a (a >= 4): the hard-wired radices only.
+static int bluestein_length(int need) {
+  int best = 0;
+  for (int odd : {1, 3, 5}) {
+    int L = odd * 16;
+    while (L < need) L <<= 1;
+    if (best == 0 || L < best) best = L;
+  }
+  return best;
+}
+
+// Chooses the transform of the M packed points (mixed radix, or Bluestein over a power of two
+// when M has a large prime factor), fills the pass tables and uploads the twiddles.
+// SB_FFT_BLUESTEIN=0 / 1 forces the choice (measurement and tests).
+static bool build_fft_plan(Geometry* G) {
+  GeoK& g = G->k;
+  const int L = bluestein_length(2 * g.M - 1);
+  bool bluestein = largest_prime_factor(g.M) >= 32;
+  if (const char* e = getenv("SB_FFT_BLUESTEIN")) bluestein = *e == '1' ? true : (*e == '0' ? false : bluestein);
+  if (2 * sizeof(float2) * (size_t)L > 200 * 1024 || L > 65536) bluestein = false;
+  g.bl_L = bluestein ? L : 0;
+  g.fft_len = bluestein ? L : g.M;
+  factorize(g.fft_len, g.fac, &g.nfac);
+  fill_passes(g);
+  const int FL = g.fft_len;
+  std::vector<float2> tw(FL);
+  for (int k = 0; k < FL; k++) {
+    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)FL;
+    tw[k] = make_float2((float)cosl(a), (float)sinl(a));
+  }
+  g.tw = upload(G, tw);
+  g.twg = upload(G, generic_roots(g));
+  if (!g.tw || !g.twg) return false;
+  if (bluestein) {
+    const int M = g.M;
+    std::vector<float2> w(M);
+    std::vector<double> cr(M), ci(M), cosL(L);
+    for (int k = 0; k < L; k++)
+      cosL[k] = (double)cosl(2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)L);
+    for (int n = 0; n < M; n++) {
+      const long long q = ((long long)n * n) % (2LL * M);      // n^2 mod 2M: the phase stays exact
+      const long double a = -3.14159265358979323846264338327950288L * (long double)q / (long double)M;
+      const double c = (double)cosl(a), sn = (double)sinl(a);
+      w[n] = make_float2((float)c, (float)sn);
+      cr[n] = c; ci[n] = -sn;                                  // b[+-n] = conj(w[n])
+    }
+    // b is symmetric in n, so its DFT is b[0] + 2 sum_{n >= 1} b[n] cos(2 pi n k / L): L M terms
+    std::vector<float2> B(L);
+    for (int k = 0; k < L; k++) {
+      double sr = cr[0], si = ci[0];
+      long long idx = 0;
+      for (int n = 1; n < M; n++) {
+        idx += k;
+        if (idx >= L) idx -= L;
+        sr += 2.0 * cr[n] * cosL[idx];
+        si += 2.0 * ci[n] * cosL[idx];
+      }
+      B[k] = make_float2((float)(sr / L), (float)(si / L));
+    }
+    g.bl_w = upload(G, w);
+    g.bl_B = upload(G, B);
+    if (!g.bl_w || !g.bl_B) return false;
+  }
+  return true;
 }
 
 // spl_reference_value: absolute_hearing_thresholds.c:86-89,118-139.  The
@@ -174,8 +252,6 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
   g.M = (int)(N / 2);
   g.cp = (int)(N / 2 - frame / 2);
   g.frame_p = (g.frame + 3) & ~3;
-  factorize(g.M, g.fac, &g.nfac);
-  fill_passes(g);
 
   // periodic Hann over `frame` (spectral_utils.c:34-37, general_utils.c:26-31)
   const float pi = 3.14159265358979323846f;
@@ -191,12 +267,8 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
   for (uint32_t k = 0; k < frame; k++) sum += win[k] * win[k];
   g.scale = (sum < 1.1920929e-7f) ? 1.f : sum * ((float)N / (float)g.hop);
 
-  // FFT twiddles
-  std::vector<float2> tw(g.M), twn(g.M + 1);
-  for (int k = 0; k < g.M; k++) {
-    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.M;
-    tw[k] = make_float2((float)cosl(a), (float)sinl(a));
-  }
+  // twiddles of the real <-> packed complex split (the transform's own: build_fft_plan)
+  std::vector<float2> twn(g.M + 1);
   for (int k = 0; k <= g.M; k++) {
     long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.N;
     twn[k] = make_float2((float)cosl(a), (float)sinl(a));
@@ -298,16 +370,15 @@ const Geometry* get_geometry(uint32_t sample_rate, float frame_ms) {
     }
   }
 
+  const bool plan_ok = build_fft_plan(G);
   g.win = upload(G, win);
-  g.tw = upload(G, tw);
   g.twn = upload(G, twn);
-  g.twg = upload(G, generic_roots(g));
   g.abs_thr_spl = upload(G, thr_spl);
   g.abs_thr_lin = upload(G, thr_lin);
   g.cband = upload(G, cband);
   g.veto_t = upload(G, veto_t);
   g.band_of_bin = upload(G, bob);
-  if (!g.win || !g.tw || !g.twn || !g.twg || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
+  if (!plan_ok || !g.win || !g.tw || !g.twn || !g.twg || !g.abs_thr_spl || !g.abs_thr_lin || !g.cband ||
       !g.veto_t || !g.band_of_bin) {
     set_error("geometry upload", cudaGetLastError(), __FILE__, __LINE__);
     for (void* p : G->dev_allocs) dev_free(p);
@@ -338,23 +409,16 @@ Geometry* make_fft_geometry(int fft_size) {
   g.cp = 0;
   g.frame_p = (g.frame + 3) & ~3;
   g.scale = 1.0f;
-  factorize(g.M, g.fac, &g.nfac);
-  fill_passes(g);
   std::vector<float> win(fft_size, 1.0f);
-  std::vector<float2> tw(g.M), twn(g.M + 1);
-  for (int k = 0; k < g.M; k++) {
-    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.M;
-    tw[k] = make_float2((float)cosl(a), (float)sinl(a));
-  }
+  std::vector<float2> twn(g.M + 1);
   for (int k = 0; k <= g.M; k++) {
     long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)g.N;
     twn[k] = make_float2((float)cosl(a), (float)sinl(a));
   }
+  const bool plan_ok = build_fft_plan(G);
   g.win = upload(G, win);
-  g.tw = upload(G, tw);
   g.twn = upload(G, twn);
-  g.twg = upload(G, generic_roots(g));
-  if (!g.win || !g.tw || !g.twn || !g.twg) {
+  if (!plan_ok || !g.win || !g.tw || !g.twn || !g.twg) {
     free_geometry(G);
     return nullptr;
   }

@@ -12,7 +12,10 @@
 // between two shared-memory buffers (radix 4, 2, 5 and 3 hard-wired, any other
 // prime factor through a generic O(r) per output butterfly in double), and split into the
 // N/2+1 bins of the real transform.  The frame sizes of the library are not
-// powers of two (N = frame + 800), hence the runtime factor list.
+// powers of two (N = frame + 800), hence the runtime factor list.  When M has a
+// prime factor >= 32 (44.1 kHz / 50 ms: M = 1503 = 3^2 167) the M points go
+// through Bluestein's convolution over a length 2^a, 3 2^a or 5 2^a instead
+// (fft_points below; plan and tables: build_fft_plan in sb_geometry.cu).
 #include "sb_common.h"
 
 namespace sb {
@@ -255,6 +258,46 @@ __device__ float2* stockham(float2* x, float2* y, const GeoK& g) {
   return x;
 }
 
+// DFT of the M packed points in `a` (b: second buffer of the same size), either directly or,
+// for an M with a large prime factor, as Bluestein's convolution over the power of two L:
+//   Z[k] = w[k] * sum_n (z[n] w[n]) conj(w)[k - n],   w[n] = exp(-i pi n^2 / M)
+// (forward; the unnormalised inverse conjugates w).  The convolution runs through two L-point
+// Stockham transforms; bl_B = FFT_L(conj(w) wrapped to +-n) / L is real-symmetric in n, so the
+// inverse's spectrum is conj(bl_B).  Returns the buffer holding the M results.
+template <bool INV>
+__device__ __forceinline__ float2* fft_points(float2* a, float2* b, const GeoK& g) {
+  if (g.bl_L == 0) return stockham<INV>(a, b, g);
+  const int M = g.M, L = g.bl_L;
+  const float2* __restrict__ cw = g.bl_w;
+  const float2* __restrict__ cB = g.bl_B;
+  for (int n = threadIdx.x; n < L; n += blockDim.x) {
+    float2 v = make_float2(0.f, 0.f);
+    if (n < M) {
+      float2 w = __ldg(&cw[n]);
+      if (INV) w.y = -w.y;
+      v = cmul(a[n], w);
+    }
+    a[n] = v;
+  }
+  __syncthreads();
+  float2* A = stockham<false>(a, b, g);
+  float2* other = (A == a) ? b : a;
+  for (int k = threadIdx.x; k < L; k += blockDim.x) {
+    float2 Bk = __ldg(&cB[k]);
+    if (INV) Bk.y = -Bk.y;
+    A[k] = cmul(A[k], Bk);
+  }
+  __syncthreads();
+  float2* c = stockham<true>(A, other, g);
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    float2 w = __ldg(&cw[k]);
+    if (INV) w.y = -w.y;
+    c[k] = cmul(c[k], w);
+  }
+  __syncthreads();
+  return c;
+}
+
 // ---------------------------------------------------------------------------
 // forward: frame f = xbuf[f*hop, f*hop+frame) -> Hann -> centre in N -> rFFT
 //
@@ -290,7 +333,7 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
                float* __restrict__ Xim, float* __restrict__ P) {
   extern __shared__ __align__(16) float2 smem[];
   float2* a = smem;
-  float2* b = smem + g.M;
+  float2* b = smem + g.fft_len;
   const int f = blockIdx.x;
   const float* __restrict__ src = xbuf + (size_t)f * g.hop;
   const float* __restrict__ win = g.win;
@@ -323,7 +366,7 @@ forward_kernel(const GeoK g, const float* __restrict__ xbuf, float* __restrict__
     }
   }
   __syncthreads();
-  const float2* Z = stockham<false>(a, b, g);
+  const float2* Z = fft_points<false>(a, b, g);
   // split into the real spectrum; halfcomplex bin k <-> (Xre[k], Xim[k])
   float* __restrict__ re = Xre + (size_t)f * g.Kp;
   float* __restrict__ im = Xim + (size_t)f * g.Kp;
@@ -360,7 +403,7 @@ inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restr
                float* __restrict__ synth) {
   extern __shared__ __align__(16) float2 smem[];
   float2* a = smem;
-  float2* b = smem + g.M;
+  float2* b = smem + g.fft_len;
   const int f = blockIdx.x;
   const int M = g.M;
   const float* __restrict__ re = Yre + (size_t)f * g.Kp;
@@ -421,7 +464,7 @@ inverse_kernel(const GeoK g, const float* __restrict__ Yre, const float* __restr
     }
   }
   __syncthreads();
-  const float2* z = stockham<true>(a, b, g);
+  const float2* z = fft_points<true>(a, b, g);
   // OUTPUT window then divide by scale (stft_windows.c:120-137), crop (fft_transform.c:184-201)
   float* __restrict__ out = synth + (size_t)f * g.frame_p;
   const float* __restrict__ win = g.win;
@@ -496,7 +539,7 @@ bool launch_forward(const GeoK& g, const float* xbuf, int frames, float* Xre, fl
                     float* P, cudaStream_t st) {
   KTimer kt_(kcForward, st);
   if (frames <= 0) return true;
-  const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
+  const size_t smem = 2 * sizeof(float2) * (size_t)g.fft_len;
   if (fft_vec_ok(g) && ((uintptr_t)xbuf & 7) == 0) {
     if (!set_fft_smem((const void*)forward_kernel<true>, smem)) return false;
     forward_kernel<true><<<frames, g.fft_threads, smem, st>>>(g, xbuf, Xre, Xim, P);
@@ -512,7 +555,7 @@ bool launch_inverse(const GeoK& g, const float* Yre, const float* Yim, int frame
                     float* synth, cudaStream_t st) {
   KTimer kt_(kcInverse, st);
   if (frames <= 0) return true;
-  const size_t smem = 2 * sizeof(float2) * (size_t)g.M;
+  const size_t smem = 2 * sizeof(float2) * (size_t)g.fft_len;
   if (fft_vec_ok(g)) {
     if (!set_fft_smem((const void*)inverse_kernel<true>, smem)) return false;
     inverse_kernel<true><<<frames, g.fft_threads, smem, st>>>(g, Yre, Yim, synth);
