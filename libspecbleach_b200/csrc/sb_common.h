@@ -77,8 +77,8 @@ struct GeoK {            // POD copied into kernel parameters (constant bank)
   int pass_l[14], pass_s[14], pass_tstep[14], pass_nbf[14];
   unsigned pass_smagic[14], pass_nbfmagic[14];
   int fft_threads;            // CTA size of the FFT kernels (fill_passes: fewest idle warp rounds)
-  // Length the Stockham passes above work on: M, or -- when M has a prime factor >= 32 (N = 3006 =
-  // 2 3^2 167 at 44.1 kHz / 50 ms) -- the power of two L >= 2M - 1 of Bluestein's chirp-z form,
+  // Length the Stockham passes above work on: M, or -- when M has a large prime factor (N = 3006 =
+  // 2 3^2 167 at 44.1 kHz / 50 ms; the rule is build_fft_plan's work estimate) -- the power of two L >= 2M - 1 of Bluestein's chirp-z form,
   // in which the M-point DFT is a cyclic convolution of length L: two L-point FFTs and three
   // pointwise products instead of an O(r) sum per output of the radix-r pass.
   int fft_len;                // M or L

@@ -118,13 +118,6 @@ static std::vector<double2> generic_roots(GeoK& g) {
   return t;
 }
 
-static int largest_prime_factor(int m) {
-  int best = 1;
-  for (int p = 2; p * p <= m; p++)
-    while (m % p == 0) { best = p; m /= p; }
-  return m > 1 ? m : best;
-}
-
 // Smallest length >= need of the form 2^a, 3 2^a or 5 2^a (a >= 4): the hard-wired radices only.
 static int bluestein_length(int need) {
   int best = 0;
@@ -142,7 +135,19 @@ static int bluestein_length(int need) {
 static bool build_fft_plan(Geometry* G) {
   GeoK& g = G->k;
   const int L = bluestein_length(2 * g.M - 1);
-  bool bluestein = largest_prime_factor(g.M) >= 32;
+  // Work of the generic passes (a pair of outputs per (r - 1) / 2 terms of four double FMAs, FP64
+  // at half the FP32 rate: ~4 M r FP32-equivalent FMAs per pass of radix r) against the two
+  // L-point transforms (~5 L log2 L), with the factor 2 that the measured kernels show between
+  // the two forms (M = 1503: model 5.6x, kernel 2.6x).  M = 1503 (167), 907 (prime), 2605 (521):
+  // Bluestein; 841 (29 x 29), 4810 (37): generic.
+  double generic_work = 0.0;
+  {
+    int fac[14], nfac = 0;
+    factorize(g.M, fac, &nfac);
+    for (int f = 0; f < nfac; f++)
+      if (fac[f] != 2 && fac[f] != 3 && fac[f] != 4 && fac[f] != 5) generic_work += 4.0 * g.M * fac[f];
+  }
+  bool bluestein = generic_work > 2.0 * 5.0 * L * log2((double)L);
   if (const char* e = getenv("SB_FFT_BLUESTEIN")) bluestein = *e == '1' ? true : (*e == '0' ? false : bluestein);
   if (2 * sizeof(float2) * (size_t)L > 200 * 1024 || L > 65536) bluestein = false;
   g.bl_L = bluestein ? L : 0;

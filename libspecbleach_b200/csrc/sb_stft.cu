@@ -13,7 +13,7 @@
 // prime factor through a generic O(r) per output butterfly in double), and split into the
 // N/2+1 bins of the real transform.  The frame sizes of the library are not
 // powers of two (N = frame + 800), hence the runtime factor list.  When M has a
-// prime factor >= 32 (44.1 kHz / 50 ms: M = 1503 = 3^2 167) the M points go
+// large prime factor (44.1 kHz / 50 ms: M = 1503 = 3^2 167) the M points go
 // through Bluestein's convolution over a length 2^a, 3 2^a or 5 2^a instead
 // (fft_points below; plan and tables: build_fft_plan in sb_geometry.cu).
 #include "sb_common.h"

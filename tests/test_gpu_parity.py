@@ -23,7 +23,7 @@ def synth(seconds, sr, seed):
 
 
 # ----------------------------- single kernels --------------------------------
-@pytest.mark.parametrize("n", [3200, 3006, 8192, 1682, 2564, 1760, 3008, 6010])
+@pytest.mark.parametrize("n", [3200, 3006, 8192, 1682, 2564, 1760, 3008, 6010, 5114, 9620, 1814])
 def test_rfft_kernels(gpu, n):
     """forward_kernel / inverse_kernel vs numpy pocketfft in double (fft_transform.c:98-103,
     tests/test_fft.c:79-105: forward o backward = N*x within 1e-4)."""
